@@ -1,0 +1,150 @@
+/* libgspb200 -- C ABI of the B200-native Chebyshev graph-filtering engine.
+ *
+ * The reference (PyGSP 0.6.1) has no FFI: its seam for this path is the Python
+ * call boundary, below which every operation is a call into SciPy's compiled
+ * sparsetools / ARPACK.  Each entry point below replaces one such call; the
+ * comment names the reference line it stands in for.  Conventions:
+ *
+ *   - every array argument is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises (the caller owns synchronisation);
+ *   - return value 0 = OK, negative = error (-1 bad argument, -2 CUDA error,
+ *     -3 unsupported); the message is available from gsp_last_error()
+ *     (thread-local).  Nothing throws across the boundary;
+ *   - the callee never frees or keeps caller memory.  Outputs whose size is
+ *     data dependent come as a *_count / *_fill pair: the count pass writes
+ *     the output indptr (whose last element is the nnz to allocate);
+ *   - CSR index arrays are int32 (as SciPy's for nnz < 2^31), values are
+ *     float (_f32) or double (_f64); the weighted degree `dw` is always double.
+ */
+#ifndef GSPB200_H_
+#define GSPB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSPB200_ABI_VERSION 1
+
+int gsp_abi_version(void);
+const char* gsp_last_error(void);
+int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------ filter --
+ * gsp_cheby_op_*: pygsp/filters/approximations.py:58-114 `cheby_op(G, c, signal)`.
+ *   L = (indptr, indices, data) n x n CSR; lmax = G.lmax; coeffs_host is the
+ *   (nscales, m) row-major coefficient matrix (m = order + 1 >= 2, else the
+ *   reference's TypeError condition is reported as -1); x is (n, nsig)
+ *   row-major; r receives (nscales, n, nsig) = the reference's filter-major
+ *   (nscales*n, nsig) block; work holds 2*n*nsig elements.  x is not modified.
+ * gsp_cheby_step_*: one fused recurrence step on rows [row_begin, row_end)
+ *   x_new = alpha*(L x_cur) + beta*x_cur + gamma*x_old ;  r_i (+)= ck[i]*x_new
+ *   (first != 0: r_i = c0[i]/2 * x_cur + ck[i] * x_new, x_old unused).
+ *   x_new may alias x_old.  Stands for approximations.py:99-103 (first) and
+ *   :107-112 (k >= 2).  Used directly by the vertex-partitioned multi-GPU path,
+ *   where column indices address a local x_cur that has halo rows appended.
+ * gsp_spmm_*: y = L x, scipy `csr_matrix.dot` (approximations.py:99, graph.py:955).
+ */
+int gsp_cheby_op_f32(int64_t n, const int32_t* indptr, const int32_t* indices,
+                     const float* data, double lmax, const double* coeffs_host, int nscales,
+                     int m, const float* x, int64_t nsig, float* r, float* work, void* stream);
+int gsp_cheby_op_f64(int64_t n, const int32_t* indptr, const int32_t* indices,
+                     const double* data, double lmax, const double* coeffs_host, int nscales,
+                     int m, const double* x, int64_t nsig, double* r, double* work, void* stream);
+int gsp_cheby_step_f32(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
+                       const int32_t* indices, const float* data, const float* x_cur,
+                       const float* x_old, float* x_new, float* r, int64_t r_rows,
+                       int64_t nsig, int nscales, const double* ck_host, const double* c0_host,
+                       double alpha, double beta, double gamma, void* stream);
+int gsp_cheby_step_f64(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
+                       const int32_t* indices, const double* data, const double* x_cur,
+                       const double* x_old, double* x_new, double* r, int64_t r_rows,
+                       int64_t nsig, int nscales, const double* ck_host, const double* c0_host,
+                       double alpha, double beta, double gamma, void* stream);
+int gsp_spmm_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
+                 const float* x, int64_t nsig, float* y, void* stream);
+int gsp_spmm_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                 const double* x, int64_t nsig, double* y, void* stream);
+
+/* ------------------------------------------------------------------- lmax ---
+ * gsp_lanczos_*: pygsp/graphs/graph.py:911-917 (scipy eigsh -> ARPACK).
+ *   Runs Lanczos iterations [j0, j1) on L.  V3 holds 3*n elements, scal_dev
+ *   2*cap+1 doubles: alpha[0..cap) | beta[0..cap) | scratch.  j0 == 0 seeds the
+ *   start vector from `seed` (counter-based, reproducible).  The host reads
+ *   alpha/beta back and diagonalises the tridiagonal matrix.
+ */
+int gsp_lanczos_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
+                    float* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
+                    void* stream);
+int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                    double* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
+                    void* stream);
+
+/* ------------------------------------------------------------------ graph ---
+ * gsp_csr_inspect_*   graph.py:111-122  NaN / Inf / negative / self-loop checks.
+ *     stats_dev[8] (int64): [0] NaN [1] Inf [2] negative [3] non-zero diagonal
+ *     [4] stored zeros [5] unsorted-or-duplicate columns [6] column out of range.
+ * gsp_csr_compact_*   graph.py:128      eliminate_zeros().
+ * gsp_csr_asymmetry_* graph.py:403-405  (W != W.T).nnz: entries whose mirror differs.
+ * gsp_csr_transpose_* W.T as sorted CSR (needed by the directed-graph branches).
+ * gsp_csr_average_*   utils.py:247-248  (A + B)/2, exact zeros dropped.
+ * gsp_degree_*        graph.py:772-781, 830-838  d and dw (pass the transpose for
+ *     a directed graph, else NULL); d may be NULL.
+ * gsp_laplacian_*     graph.py:618-628  lap_type 0 combinatorial, 1 normalized; the
+ *     input must be the SYMMETRIC adjacency ((W+W.T)/2 for a directed graph).
+ *     indptr/indices of the result are bit-identical to SciPy's.
+ * gsp_spectral_bounds_* graph.py:939-958  out5_dev (double): max W, max dw,
+ *     max(dw_s+dw_t) over edges, max(dw+(Ws dw)/dw), #NaN terms of the latter.
+ * gsp_gather_rows_* / gsp_scatter_rows_*  dst[i,:] = src[idx[i],:] / dst[idx[i],:] = src[i,:]
+ *     (vertex reordering in and out, halo packing).
+ */
+#define GSPB200_DECLARE_GRAPH_API(SUF, T)                                                        \
+  int gsp_csr_inspect_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,            \
+                            const T* data, int64_t* stats_dev, void* stream);                    \
+  int gsp_csr_compact_count_##SUF(int64_t n, const int32_t* indptr, const T* data,               \
+                                  int32_t* out_indptr, void* stream);                            \
+  int gsp_csr_compact_fill_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,       \
+                                 const T* data, const int32_t* out_indptr, int32_t* out_indices, \
+                                 T* out_data, void* stream);                                     \
+  int gsp_csr_asymmetry_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,          \
+                              const T* data, int64_t* count_dev, void* stream);                  \
+  int gsp_csr_transpose_##SUF(int64_t n, int64_t nnz, const int32_t* indptr,                     \
+                              const int32_t* indices, const T* data, int32_t* t_indptr,          \
+                              int32_t* t_indices, T* t_data, void* stream);                      \
+  int gsp_csr_average_count_##SUF(int64_t n, const int32_t* a_indptr, const int32_t* a_indices,  \
+                                  const T* a_data, const int32_t* b_indptr,                      \
+                                  const int32_t* b_indices, const T* b_data, int32_t* s_indptr,  \
+                                  void* stream);                                                 \
+  int gsp_csr_average_fill_##SUF(int64_t n, const int32_t* a_indptr, const int32_t* a_indices,   \
+                                 const T* a_data, const int32_t* b_indptr,                       \
+                                 const int32_t* b_indices, const T* b_data,                      \
+                                 const int32_t* s_indptr, int32_t* s_indices, T* s_data,         \
+                                 void* stream);                                                  \
+  int gsp_degree_##SUF(int64_t n, const int32_t* indptr, const T* data,                          \
+                       const int32_t* t_indptr, const T* t_data, double* dw, double* d,          \
+                       void* stream);                                                            \
+  int gsp_laplacian_count_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,        \
+                                const T* data, const double* dw, int lap_type,                   \
+                                int32_t* l_indptr, void* stream);                                \
+  int gsp_laplacian_fill_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,         \
+                               const T* data, const double* dw, int lap_type,                    \
+                               const int32_t* l_indptr, int32_t* l_indices, T* l_data,           \
+                               void* stream);                                                    \
+  int gsp_spectral_bounds_##SUF(int64_t n, const int32_t* w_indptr, const int32_t* w_indices,    \
+                                const T* w_data, const int32_t* s_indptr,                        \
+                                const int32_t* s_indices, const T* s_data, const double* dw,     \
+                                double* out5_dev, void* stream);                                 \
+  int gsp_gather_rows_##SUF(int64_t rows, const int64_t* idx, const T* src, int64_t width,       \
+                            T* dst, void* stream);                                               \
+  int gsp_scatter_rows_##SUF(int64_t rows, const int64_t* idx, const T* src, int64_t width,      \
+                             T* dst, void* stream);
+
+GSPB200_DECLARE_GRAPH_API(f32, float)
+GSPB200_DECLARE_GRAPH_API(f64, double)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPB200_H_ */

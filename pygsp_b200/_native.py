@@ -1,0 +1,111 @@
+"""ctypes binding of libgspb200.so (the C ABI declared in include/gspb200.h).
+
+There is NO fallback: if the shared library cannot be built or loaded, or no
+CUDA device is present when a kernel is requested, the call raises.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "gspb200.h")
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def header_symbols():
+    """Every function name include/gspb200.h declares (macro-expanded)."""
+    text = open(_HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    macro = re.search(r"#define GSPB200_DECLARE_GRAPH_API\(SUF, T\)(.*?)\n\n", text, flags=re.S)
+    templ = re.findall(r"\b(gsp_[a-z0-9_]+_)##SUF", macro.group(1)) if macro else []
+    body = text.replace(macro.group(0), "") if macro else text
+    out = set(re.findall(r"\b(gsp_[a-z0-9_]+)\s*\(", body))
+    for t in templ:
+        out.add(t + "f32")
+        out.add(t + "f64")
+    return sorted(out)
+
+
+def lib():
+    """Load (building in-tree if needed) the shared library."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path) or os.environ.get("GSPB200_REBUILD"):
+            path = _build.build()
+        try:
+            _lib = ctypes.CDLL(path)
+        except OSError as exc:   # pragma: no cover
+            raise NativeError("cannot load %s: %s" % (path, exc))
+        _lib.gsp_last_error.restype = ctypes.c_char_p
+        _lib.gsp_abi_version.restype = ctypes.c_int
+        if _lib.gsp_abi_version() != 1:
+            raise NativeError("libgspb200 ABI mismatch")
+    return _lib
+
+
+def _arg(a):
+    """torch tensor -> device pointer; None -> NULL; numpy -> host pointer."""
+    if a is None:
+        return ctypes.c_void_p(0)
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    return a
+
+
+def call(name, *args):
+    fn = getattr(lib(), name)
+    fn.restype = ctypes.c_int
+    rc = fn(*[_arg(a) for a in args])
+    if rc != 0:
+        msg = lib().gsp_last_error().decode(errors="replace")
+        if rc == -1 and "invalid shape" in msg:
+            raise TypeError("The coefficients have an invalid shape")
+        raise NativeError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def suffix(dtype):
+    import torch
+    if dtype in (torch.float32, np.float32) or dtype == np.dtype("float32"):
+        return "f32"
+    if dtype in (torch.float64, np.float64) or dtype == np.dtype("float64"):
+        return "f64"
+    raise TypeError("unsupported dtype %r (float32 / float64 only)" % (dtype,))
+
+
+def i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def i32(v):
+    return ctypes.c_int(int(v))
+
+
+def u64(v):
+    return ctypes.c_uint64(int(v))
+
+
+def f64(v):
+    return ctypes.c_double(float(v))
+
+
+def stream_ptr(device=None):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError("pygsp_b200 needs a CUDA device (B200): there is no CPU fallback")
+    return torch

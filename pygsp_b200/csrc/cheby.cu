@@ -1,0 +1,351 @@
+// Chebyshev recurrence on a CSR Laplacian -- the hot path.
+//
+// Replaces, for the path pygsp/filters/approximations.py:58-114 (cheby_op):
+//   * scipy.sparse._sparsetools.csr_matvecs   (approximations.py:99,107)
+//   * the dense "- twf_old" temporary          (approximations.py:107)
+//   * the fancy-indexed r[tmpN + N*i] += c*T   (approximations.py:108-109)
+// by ONE fused kernel per recurrence step:
+//   x_new = alpha * (L x_cur) + beta * x_cur + gamma * x_old
+//   r_i   = (first ? c_i0/2 * x_cur : r_i) + c_ik * x_new         i < nscales
+// with alpha = 4/lmax, beta = -2, gamma = -1 (first step: 2/lmax, -1, 0), so
+// the CSR of L is used as stored (the reference builds a second scaled matrix
+// "factor", approximations.py:105) and T_{k-2}/T_{k-1}/T_k make exactly one
+// trip each through HBM per step.
+//
+// Layout: signals are (N, nsig) row-major (a vertex's nsig values adjacent),
+// r is (nscales, N, nsig) -- the reference's filter-major (Nscales*N, Nsig).
+//
+// Lane mapping ("row group" kernel): G = 2^g lanes own one row, each lane a
+// VEC-wide packet (16 B) of the row's columns.  The group loads G CSR entries
+// with one coalesced access and broadcasts them with shuffles; every lane then
+// gathers its packet of x_cur[col] -- a 16*G-byte contiguous, fully coalesced
+// request per neighbour -- and accumulates in registers.  The accumulation
+// order is the stored CSR order, i.e. the order scipy uses.
+#include "common.cuh"
+#include "gspb200.h"
+
+namespace gsp {
+
+constexpr int kMaxScales = 16;   // coefficients per launch passed by value
+constexpr int kStepThreads = 256;
+
+template <typename T>
+struct StepCoef {
+  T alpha, beta, gamma;
+  T half_c0[kMaxScales];   // c[i,0]/2 (first step only)
+  T ck[kMaxScales];        // c[i,k]
+};
+
+template <typename T, int VEC, int G, bool FIRST, bool SPMM>
+__global__ void __launch_bounds__(kStepThreads)
+cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
+                    const int32_t* __restrict__ indptr,
+                    const int32_t* __restrict__ indices,
+                    const T* __restrict__ vals,
+                    const T* __restrict__ x_cur,   // rows referenced by indices
+                    const T* x_old,                // may alias x_new (row-local)
+                    T* x_new,
+                    T* __restrict__ r,             // (nscales, r_rows, nsig)
+                    int64_t r_rows, int nsig, int nscales,
+                    StepCoef<T> coef) {
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t group = (int64_t(blockIdx.x) * kStepThreads + threadIdx.x) / G;
+  const int64_t row = row_begin + group;
+  // all lanes of a group share `row`; groups never straddle a warp (G <= 32)
+  if (row >= row_end) return;
+  const unsigned lane_in_warp = threadIdx.x & 31;
+  const unsigned gmask = (G == 32) ? 0xffffffffu
+                                   : (((1u << G) - 1u) << (lane_in_warp & ~(G - 1)));
+
+  const int start = __ldg(indptr + row);
+  const int end = __ldg(indptr + row + 1);
+
+  // every lane of the group runs the same trip count (the shuffles below need
+  // the whole group); lanes past the last column are merely predicated off
+  for (int cbase = 0; cbase < nsig; cbase += G * VEC) {
+    const int c0 = cbase + lane * VEC;
+    const bool active = c0 < nsig;
+    Vec<T, VEC> acc, xo, xc;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc.v[v] = xo.v[v] = xc.v[v] = T(0);
+
+    // streaming operands first: they are in flight while the gather runs
+    if (active) {
+      if (!FIRST) xo = load_vec_stream<T, VEC>(x_old + row * nsig + c0);
+      xc = load_vec_ro<T, VEC>(x_cur + row * nsig + c0);
+    }
+
+    if (SPMM) {
+      for (int base = start; base < end; base += G) {
+        const int mine = base + lane;
+        int col = 0;
+        T val = T(0);
+        if (mine < end) {
+          col = __ldg(indices + mine);
+          val = __ldg(vals + mine);
+        }
+        const int cnt = min(G, end - base);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+          const int cj = __shfl_sync(gmask, col, j, G);
+          const T vj = __shfl_sync(gmask, val, j, G);
+          if (active) {
+            const Vec<T, VEC> xn = load_vec_ro<T, VEC>(x_cur + int64_t(cj) * nsig + c0);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc.v[v] = fma(vj, xn.v[v], acc.v[v]);
+          }
+        }
+      }
+    }
+    if (!active) continue;
+
+    Vec<T, VEC> xn;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      T t = fma(coef.alpha, acc.v[v], coef.beta * xc.v[v]);
+      if (!FIRST) t = fma(coef.gamma, xo.v[v], t);
+      xn.v[v] = t;
+    }
+    store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
+
+    for (int i = 0; i < nscales; ++i) {
+      T* rp = r + (int64_t(i) * r_rows + row) * nsig + c0;
+      Vec<T, VEC> rv;
+      if (FIRST) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          rv.v[v] = fma(coef.ck[i], xn.v[v], coef.half_c0[i] * xc.v[v]);
+      } else {
+        rv = load_vec_stream<T, VEC>(rp);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) rv.v[v] = fma(coef.ck[i], xn.v[v], rv.v[v]);
+      }
+      store_vec_stream<T, VEC>(rp, rv);
+    }
+  }
+}
+
+// r_i += c_ik * x   for filter banks wider than kMaxScales (no SpMM)
+template <typename T>
+__global__ void cheby_axpy_scales(int64_t count, const T* __restrict__ x,
+                                  T* __restrict__ r, int64_t r_stride, int nscales,
+                                  StepCoef<T> coef, bool first,
+                                  const T* __restrict__ x0) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (; i < count; i += stride) {
+    const T xv = x[i];
+    for (int s = 0; s < nscales; ++s) {
+      T* rp = r + int64_t(s) * r_stride + i;
+      *rp = first ? fma(coef.ck[s], xv, coef.half_c0[s] * x0[i]) : fma(coef.ck[s], xv, *rp);
+    }
+  }
+}
+
+template <typename T, int VEC, int G>
+static int launch_group(bool first, bool spmm, int64_t row_begin, int64_t row_end,
+                        const int32_t* indptr, const int32_t* indices, const T* vals,
+                        const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,
+                        int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0) return GSP_OK;
+  const int64_t blocks = ceil_div(rows * G, kStepThreads);
+  GSP_REQUIRE(blocks < (int64_t(1) << 31), "row range too large for one launch");
+  dim3 grid((unsigned)blocks), block(kStepThreads);
+#define GSP_GO(F, S)                                                                   \
+  cheby_step_rowgroup<T, VEC, G, F, S><<<grid, block, 0, st>>>(                        \
+      row_begin, row_end, indptr, indices, vals, x_cur, x_old, x_new, r, r_rows, nsig, \
+      nscales, coef)
+  if (first && spmm) GSP_GO(true, true);
+  else if (first) GSP_GO(true, false);
+  else if (spmm) GSP_GO(false, true);
+  else GSP_GO(false, false);
+#undef GSP_GO
+  GSP_LAUNCH_CHECK("cheby_step_rowgroup");
+  return GSP_OK;
+}
+
+template <typename T, int VEC>
+static int launch_vec(int groups_needed, bool first, bool spmm, int64_t rb, int64_t re,
+                      const int32_t* indptr, const int32_t* indices, const T* vals,
+                      const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,
+                      int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st) {
+#define GSP_CASE(GG)                                                                     \
+  return launch_group<T, VEC, GG>(first, spmm, rb, re, indptr, indices, vals, x_cur,     \
+                                  x_old, x_new, r, r_rows, nsig, nscales, coef, st)
+  if (groups_needed <= 1) GSP_CASE(1);
+  if (groups_needed <= 2) GSP_CASE(2);
+  if (groups_needed <= 4) GSP_CASE(4);
+  if (groups_needed <= 8) GSP_CASE(8);
+  if (groups_needed <= 16) GSP_CASE(16);
+  GSP_CASE(32);
+#undef GSP_CASE
+}
+
+template <typename T> struct MaxVec;
+template <> struct MaxVec<float> { static constexpr int value = 4; };
+template <> struct MaxVec<double> { static constexpr int value = 2; };
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// One recurrence step over rows [rb, re).  Handles any nsig / nscales.
+template <typename T>
+int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
+               const int32_t* indices, const T* vals, const T* x_cur, const T* x_old,
+               T* x_new, T* r, int64_t r_rows, int nsig, int nscales, const double* ck,
+               const double* c0, double alpha, double beta, double gamma, cudaStream_t st) {
+  constexpr int MV = MaxVec<T>::value;
+  const bool vec_ok = (nsig % MV == 0) && aligned16(x_cur) && aligned16(x_new) &&
+                      aligned16(r) && (first || aligned16(x_old));
+  for (int s0 = 0; s0 < nscales || s0 == 0; s0 += kMaxScales) {
+    const int ns = min(kMaxScales, nscales - s0);
+    StepCoef<T> coef;
+    coef.alpha = T(alpha);
+    coef.beta = T(beta);
+    coef.gamma = T(gamma);
+    for (int i = 0; i < kMaxScales; ++i) {
+      coef.ck[i] = i < ns ? T(ck[s0 + i]) : T(0);
+      coef.half_c0[i] = (first && i < ns) ? T(0.5 * c0[s0 + i]) : T(0);
+    }
+    T* rs = r + int64_t(s0) * r_rows * nsig;
+    if (s0 == 0) {
+      int rc;
+      if (vec_ok)
+        rc = launch_vec<T, MV>((nsig + MV - 1) / MV, first, true, rb, re, indptr, indices,
+                               vals, x_cur, x_old, x_new, rs, r_rows, nsig, ns, coef, st);
+      else
+        rc = launch_vec<T, 1>(nsig, first, true, rb, re, indptr, indices, vals, x_cur,
+                              x_old, x_new, rs, r_rows, nsig, ns, coef, st);
+      if (rc != GSP_OK) return rc;
+    } else {
+      // remaining scales of a wide bank: r_i (+)= c_ik * x_new, no second SpMM
+      const int64_t count = (re - rb) * nsig;
+      if (count > 0) {
+        const int blocks = (int)std::min<int64_t>(ceil_div(count, 256), int64_t(sm_count()) * 16);
+        cheby_axpy_scales<T><<<blocks, 256, 0, st>>>(
+            count, x_new + rb * nsig, rs + rb * nsig, r_rows * nsig, ns, coef, first,
+            x_cur + rb * nsig);
+        GSP_LAUNCH_CHECK("cheby_axpy_scales");
+      }
+    }
+    if (nscales == 0) break;
+  }
+  return GSP_OK;
+}
+
+// Full operator (approximations.py:58-114): K = m-1 fused steps on `stream`.
+template <typename T>
+int cheby_op(int64_t n, const int32_t* indptr, const int32_t* indices, const T* vals,
+             double lmax, const double* coeffs, int nscales, int m, const T* x, int nsig,
+             T* r, T* work, cudaStream_t st) {
+  GSP_REQUIRE(n >= 0 && nsig >= 1 && nscales >= 1, "bad sizes");
+  GSP_REQUIRE(m >= 2, "The coefficients have an invalid shape");   // approximations.py:83-84
+  GSP_REQUIRE(lmax > 0 && lmax == lmax, "lmax must be positive");
+  if (n == 0) return GSP_OK;
+  double ck[1024], c0[1024];
+  GSP_REQUIRE(nscales <= 1024, "at most 1024 filters per call");
+  T* buf[2] = {work, work + n * int64_t(nsig)};
+  const T* t_old = x;
+  const T* t_cur = x;
+  for (int k = 1; k < m; ++k) {
+    for (int i = 0; i < nscales; ++i) {
+      ck[i] = coeffs[int64_t(i) * m + k];
+      c0[i] = coeffs[int64_t(i) * m];
+    }
+    int rc;
+    if (k == 1) {
+      // T_1 = (L x - a x)/a = (2/lmax) L x - x ; r_i = c_i0/2 T_0 + c_i1 T_1
+      rc = cheby_step<T>(true, 0, n, indptr, indices, vals, x, nullptr, buf[0], r, n, nsig,
+                         nscales, ck, c0, 2.0 / lmax, -1.0, 0.0, st);
+      t_cur = buf[0];
+    } else {
+      // T_k = (4/lmax) L T_{k-1} - 2 T_{k-1} - T_{k-2}, written over T_{k-2}
+      // (row-local) except for k == 2 where T_0 is the caller's input.
+      T* dst = (k == 2) ? buf[1] : const_cast<T*>(t_old);
+      rc = cheby_step<T>(false, 0, n, indptr, indices, vals, t_cur, t_old, dst, r, n, nsig,
+                         nscales, ck, c0, 4.0 / lmax, -2.0, -1.0, st);
+      t_old = t_cur;
+      t_cur = dst;
+    }
+    if (rc != GSP_OK) return rc;
+  }
+  return GSP_OK;
+}
+
+// y = A x for a block of vectors (no recurrence, no r): used by Lanczos and
+// exposed for callers that only need the product (learning.py CG, "next").
+template <typename T>
+int spmm_plain(int64_t n, const int32_t* indptr, const int32_t* indices, const T* vals,
+               const T* x, int nsig, T* y, cudaStream_t st) {
+  // x_new = 1 * (A x) + 0 * x ; FIRST form with nscales = 0 touches no r
+  double none = 0;
+  return cheby_step<T>(true, 0, n, indptr, indices, vals, x, nullptr, y, y, n, nsig, 0, &none,
+                       &none, 1.0, 0.0, 0.0, st);
+}
+
+template int cheby_step<float>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
+                               const float*, const float*, const float*, float*, float*,
+                               int64_t, int, int, const double*, const double*, double,
+                               double, double, cudaStream_t);
+template int cheby_step<double>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
+                                const double*, const double*, const double*, double*, double*,
+                                int64_t, int, int, const double*, const double*, double,
+                                double, double, cudaStream_t);
+
+}  // namespace gsp
+
+// ------------------------------- C ABI ------------------------------------
+extern "C" {
+
+int gsp_cheby_op_f32(int64_t n, const int32_t* indptr, const int32_t* indices,
+                     const float* data, double lmax, const double* coeffs_host, int nscales,
+                     int m, const float* x, int64_t nsig, float* r, float* work, void* stream) {
+  GSP_REQUIRE(nsig <= (1 << 20), "nsig too large");
+  return gsp::cheby_op<float>(n, indptr, indices, data, lmax, coeffs_host, nscales, m, x,
+                              (int)nsig, r, work, gsp::as_stream(stream));
+}
+
+int gsp_cheby_op_f64(int64_t n, const int32_t* indptr, const int32_t* indices,
+                     const double* data, double lmax, const double* coeffs_host, int nscales,
+                     int m, const double* x, int64_t nsig, double* r, double* work,
+                     void* stream) {
+  GSP_REQUIRE(nsig <= (1 << 20), "nsig too large");
+  return gsp::cheby_op<double>(n, indptr, indices, data, lmax, coeffs_host, nscales, m, x,
+                               (int)nsig, r, work, gsp::as_stream(stream));
+}
+
+int gsp_cheby_step_f32(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
+                       const int32_t* indices, const float* data, const float* x_cur,
+                       const float* x_old, float* x_new, float* r, int64_t r_rows,
+                       int64_t nsig, int nscales, const double* ck_host,
+                       const double* c0_host, double alpha, double beta, double gamma,
+                       void* stream) {
+  return gsp::cheby_step<float>(first != 0, row_begin, row_end, indptr, indices, data, x_cur,
+                                x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host, c0_host,
+                                alpha, beta, gamma, gsp::as_stream(stream));
+}
+
+int gsp_cheby_step_f64(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
+                       const int32_t* indices, const double* data, const double* x_cur,
+                       const double* x_old, double* x_new, double* r, int64_t r_rows,
+                       int64_t nsig, int nscales, const double* ck_host,
+                       const double* c0_host, double alpha, double beta, double gamma,
+                       void* stream) {
+  return gsp::cheby_step<double>(first != 0, row_begin, row_end, indptr, indices, data, x_cur,
+                                 x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
+                                 c0_host, alpha, beta, gamma, gsp::as_stream(stream));
+}
+
+int gsp_spmm_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
+                 const float* x, int64_t nsig, float* y, void* stream) {
+  return gsp::spmm_plain<float>(n, indptr, indices, data, x, (int)nsig, y,
+                                gsp::as_stream(stream));
+}
+
+int gsp_spmm_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                 const double* x, int64_t nsig, double* y, void* stream) {
+  return gsp::spmm_plain<double>(n, indptr, indices, data, x, (int)nsig, y,
+                                 gsp::as_stream(stream));
+}
+
+}  // extern "C"

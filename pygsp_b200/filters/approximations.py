@@ -1,0 +1,151 @@
+"""Chebyshev approximation of graph filters, device side.
+
+Mirror of ``pygsp/filters/approximations.py``: ``compute_cheby_coeff`` (:9-55,
+host quadrature, K+1 scalars per filter), ``cheby_op`` (:58-114, THE hot loop)
+and ``cheby_rect`` (:117-163).  The recurrence runs in ``libgspb200``:
+one fused CUDA kernel per order (csrc/cheby.cu) instead of SciPy's
+``csr_matvecs`` + NumPy temporaries + fancy-indexed accumulation.
+"""
+import numpy as np
+
+from .. import _native as nat
+from .. import utils
+
+_logger = utils.build_logger(__name__)
+
+
+@utils.filterbank_handler
+def compute_cheby_coeff(f, m=30, N=None, *args, **kwargs):
+    r"""Chebyshev coefficients of filter ``i`` of the bank ``f`` on [0, lmax].
+
+    Chebyshev-Gauss quadrature with ``N`` (default ``m + 1``) nodes:
+    ``c[o] = 2/N sum_j g(a cos(t_j) + a) cos(o t_j)``, ``t_j = pi (j + 1/2) / N``,
+    ``a = lmax / 2``.  Evaluated on the host in float64: it is K+1 numbers and
+    must see exactly the ``G.lmax`` the device recurrence is given.
+    """
+    G = f.G
+    i = kwargs.pop("i", 0)
+    if not N:
+        N = m + 1
+    half = G.lmax / 2.0
+    theta = np.pi * (np.arange(N) + 0.5) / N
+    samples = f._kernels[i](half * np.cos(theta) + half)
+    orders = np.arange(m + 1)[:, None]
+    return (2.0 / N) * (np.cos(orders * theta[None, :]) @ samples)
+
+
+def _as_device_block(G, signal):
+    """signal -> contiguous (N, nsig) device tensor in the graph's dtype."""
+    torch = nat.require_cuda()
+    kind = "cuda"
+    if not torch.is_tensor(signal):
+        signal = torch.from_numpy(np.ascontiguousarray(np.asarray(signal)))
+        kind = "numpy"
+    elif not signal.is_cuda:
+        kind = "pinned" if signal.is_pinned() else "cpu"
+    one_d = signal.dim() == 1
+    x = signal.to(device=G.device, dtype=G.dtype, non_blocking=True)
+    x = x.reshape(x.shape[0], -1).contiguous()
+    return x, one_d, kind
+
+
+def _leave_device(t, kind):
+    torch = nat.require_cuda()
+    if kind == "cuda":
+        return t
+    if kind == "numpy":
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=(kind == "pinned"))
+    out.copy_(t, non_blocking=False)
+    return out
+
+
+def _laplacian_on_device(G):
+    """(DeviceCSR L, lmax) of any graph object offering .L / .lmax / .N.
+
+    A graph of this package already holds L in HBM.  A *reference* pygsp graph
+    (scipy ``G.L``) is uploaded once and the copy is cached on the object, so
+    that this function can stand in for ``pygsp.filters.approximations.cheby_op``.
+    """
+    from ..graphs.csr import DeviceCSR
+    L = G.L
+    if isinstance(L, DeviceCSR):
+        return L
+    torch = nat.require_cuda()
+    cached = getattr(G, "_gspb200_L", None)
+    if cached is None or cached[0] is not L:
+        dtype = getattr(G, "_gspb200_dtype", torch.float32)
+        dev = torch.device("cuda:%d" % torch.cuda.current_device())
+        cached = (L, DeviceCSR.from_scipy(L, dtype, dev))
+        G._gspb200_L = cached
+    return cached[1]
+
+
+def cheby_op_device(L, lmax, c, x):
+    """Device-to-device core: x (N, nsig) tensor -> r (Nscales, N, nsig) tensor."""
+    torch = nat.require_cuda()
+    c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+    nscales, M = c.shape
+    if M < 2:
+        raise TypeError("The coefficients have an invalid shape")
+    n, nsig = x.shape
+    c = np.ascontiguousarray(c)
+    r = torch.empty((nscales, n, nsig), dtype=L.dtype, device=L.device)
+    work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
+    with torch.cuda.device(L.device):
+        nat.call("gsp_cheby_op_" + nat.suffix(L.dtype), nat.i64(n), L.indptr, L.indices, L.data,
+                 nat.f64(lmax), c, nat.i32(nscales), nat.i32(M), x, nat.i64(nsig), r, work,
+                 nat.stream_ptr(L.device))
+    return r
+
+
+def cheby_op(G, c, signal, **kwargs):
+    r"""Chebyshev polynomial of the graph Laplacian applied to a signal block.
+
+    Same contract as the reference (approximations.py:58-114): ``c`` is one
+    coefficient vector or an (Nscales, M) array / list of vectors, ``signal``
+    is (N,) or (N, Nsig); the result is (Nscales*N,) or (Nscales*N, Nsig) with
+    filter-major row blocks.  ``M < 2`` raises TypeError.  NumPy in -> NumPy
+    out, CUDA tensor in -> CUDA tensor out.  The arithmetic type is the
+    graph's (float32 by default; the reference always computes in float64).
+    """
+    if not isinstance(c, np.ndarray):
+        c = np.array(c)
+    c = np.atleast_2d(c)
+    if c.shape[1] < 2:
+        raise TypeError("The coefficients have an invalid shape")
+    L = _laplacian_on_device(G)
+    x, one_d, kind = _as_device_block(_GraphView(L), signal)
+    if x.shape[0] != G.N:
+        raise ValueError("First dimension must be the number of vertices "
+                         "G.N = {}, got {}.".format(G.N, tuple(x.shape)))
+    r = cheby_op_device(L, G.lmax, c, x)
+    r = r.reshape(c.shape[0] * G.N, x.shape[1])
+    if one_d:
+        r = r.reshape(-1)
+    return _leave_device(r, kind)
+
+
+class _GraphView:
+    def __init__(self, L):
+        self.device, self.dtype = L.device, L.dtype
+
+
+def cheby_rect(G, bounds, signal, **kwargs):
+    r"""Ideal band-pass [bounds[0], bounds[1]] by closed-form Chebyshev coefficients.
+
+    Reference: approximations.py:117-163.  The expansion coefficients of the
+    rectangle are c_0/2 = (b1-b2)/pi, c_k = 2/(k pi) (sin k b1 - sin k b2) with
+    b = arccos(2 bounds / lmax - 1); the recurrence is the one of ``cheby_op``,
+    so the same fused kernel is used with these coefficients.
+    """
+    if not (isinstance(bounds, (list, np.ndarray)) and len(bounds) == 2):
+        raise ValueError("Bounds of wrong shape.")
+    bounds = np.array(bounds, dtype=np.float64)
+    order = int(kwargs.pop("order", 30))
+    b1, b2 = np.arccos(2.0 * bounds / G.lmax - 1.0)
+    k = np.arange(1, order + 1)
+    c = np.empty(order + 1)
+    c[0] = 2.0 * (b1 - b2) / np.pi
+    c[1:] = 2.0 / (k * np.pi) * (np.sin(k * b1) - np.sin(k * b2))
+    return cheby_op(G, c, signal)

@@ -1,0 +1,148 @@
+"""``Filter``: a bank of spectral kernels applied by Chebyshev recurrence on the GPU.
+
+Mirror of the hot-path part of ``pygsp/filters/filter.py``: the container
+(:56-69), ``evaluate`` (:112-144), ``filter`` with its shape conventions
+(:146-328), ``analyze`` / ``synthesize`` (:330-348), ``localize`` (:350-391)
+and the small operators (:83-103).  ``method='exact'`` needs the dense
+eigendecomposition and is not part of this engine.
+"""
+import numpy as np
+
+from .. import _native as nat
+from .. import utils
+from ..graphs.graph import Graph
+from . import approximations
+
+_logger = utils.build_logger(__name__)
+
+
+class Filter:
+    r"""Filter bank defined by kernel functions of the graph frequencies.
+
+    Parameters
+    ----------
+    G : Graph
+    kernels : function or list of functions (one per filter, NumPy array in -> out)
+    """
+
+    def __init__(self, G, kernels):
+        self.G = G
+        try:
+            iter(kernels)
+        except TypeError:
+            kernels = [kernels]
+        self._kernels = kernels
+        self.n_features_in, self.n_features_out = (1, len(kernels))
+        self.shape = (self.n_features_out, self.n_features_in)
+        self.n_filters = self.n_features_in * self.n_features_out
+        self.Nf = self.n_filters
+
+    def _get_extra_repr(self):
+        return dict()
+
+    def __repr__(self):
+        attrs = {"in": self.n_features_in, "out": self.n_features_out}
+        attrs.update(self._get_extra_repr())
+        return "{}({})".format(type(self).__name__,
+                               ", ".join("{}={}".format(k, v) for k, v in attrs.items()))
+
+    def __len__(self):
+        return self.n_filters
+
+    def __getitem__(self, key):
+        return Filter(self.G, self._kernels[key])
+
+    def __add__(self, other):
+        if not isinstance(other, Filter):
+            return NotImplemented
+        return Filter(self.G, self._kernels + other._kernels)
+
+    def __call__(self, x):
+        if isinstance(x, Graph):
+            return Filter(x, self._kernels)
+        return self.evaluate(x)
+
+    def __matmul__(self, other):
+        return self.filter(other)
+
+    def evaluate(self, x):
+        r"""Frequency response of every kernel at ``x``: shape (Nf, *x.shape)."""
+        x = np.asanyarray(x)
+        y = np.empty([self.Nf] + list(x.shape))
+        for i, kernel in enumerate(self._kernels):
+            y[i] = kernel(x)
+        return y
+
+    def filter(self, s, method="chebyshev", order=30):
+        r"""Filter signals (analysis or synthesis) -- filter.py:146-328.
+
+        ``s`` is read as (N, N_SIGNALS, N_FEATURES).  A last dimension that is
+        neither 1 nor Nf is a signal dimension.  One input feature -> analysis:
+        every filter is applied, output (N, N_SIGNALS, Nf).  Nf input features
+        -> synthesis: filter i is applied to feature i and the results are
+        summed, output (N, N_SIGNALS).  Singleton dimensions are squeezed.
+        NumPy in -> NumPy out; CUDA tensors stay on the device.
+        """
+        torch = nat.require_cuda()
+        s = self.G._check_signal(s)
+        if method != "chebyshev":
+            if method == "exact":
+                raise NotImplementedError(
+                    "method='exact' needs the dense Fourier basis, which is outside this "
+                    "engine's path; use method='chebyshev'.")
+            raise ValueError("Unknown method {}.".format(method))
+
+        if s.ndim == 1 or s.shape[-1] not in [1, self.Nf]:
+            if s.ndim == 3:
+                raise ValueError("Third dimension (#features) should be either 1 or the number "
+                                 "of filters Nf = {}, got {}.".format(self.Nf, tuple(s.shape)))
+            s = s[..., None]
+        n_features_in = s.shape[-1]
+        if s.ndim < 3:
+            s = s[:, None, :]
+        if s.ndim > 3:
+            raise ValueError("At most 3 dimensions: #nodes x #signals x #features.")
+        n_signals = s.shape[1]
+        N = self.G.N
+
+        c = approximations.compute_cheby_coeff(self, m=order)
+        c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+        if c.shape[1] < 2:
+            raise TypeError("The coefficients have an invalid shape")
+        L = approximations._laplacian_on_device(self.G)
+        view = approximations._GraphView(L)
+
+        if n_features_in == 1:                                   # analysis
+            x, _, kind = approximations._as_device_block(view, s.reshape(N, n_signals))
+            r = approximations.cheby_op_device(L, self.G.lmax, c, x)      # (Nf, N, nsig)
+            out = r.permute(1, 2, 0)                                      # (N, nsig, Nf)
+        else:                                                    # synthesis
+            x, _, kind = approximations._as_device_block(view, s.reshape(N, -1))
+            x = x.reshape(N, n_signals, n_features_in)
+            out = torch.zeros((N, n_signals), dtype=L.dtype, device=L.device)
+            for i in range(n_features_in):
+                xi = x[:, :, i].contiguous()
+                out += approximations.cheby_op_device(L, self.G.lmax, c[i], xi)[0]
+            out = out[:, :, None]
+        out = out.squeeze()
+        return approximations._leave_device(out, kind)
+
+    def analyze(self, s, method="chebyshev", order=30):
+        r"""Alias of :meth:`filter` for single-feature input (filter.py:330-336)."""
+        if s.ndim == 3 and s.shape[-1] != 1:
+            raise ValueError("Last dimension (#features) should be 1, got {}.".format(
+                tuple(s.shape)))
+        return self.filter(s, method, order)
+
+    def synthesize(self, s, method="chebyshev", order=30):
+        r"""Alias of :meth:`filter` for Nf-feature input (filter.py:338-348)."""
+        if s.shape[-1] != self.Nf:
+            raise ValueError("Last dimension (#features) should be the number of filters "
+                             "Nf = {}, got {}.".format(self.Nf, tuple(s.shape)))
+        return self.filter(s, method, order)
+
+    def localize(self, i, **kwargs):
+        r"""Kernels localised at vertex ``i``: sqrt(N) g(L) delta_i (filter.py:350-391)."""
+        s = np.zeros(self.G.N)
+        s[i] = 1
+        return np.sqrt(self.G.N) * self.filter(s, **kwargs)

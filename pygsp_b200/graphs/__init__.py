@@ -1,0 +1,4 @@
+"""Graph object and the generators the BASELINE configurations use."""
+from .csr import DeviceCSR  # noqa: F401
+from .graph import Graph  # noqa: F401
+from .generators import Grid2d, Logo, NNGraph, Ring, Sensor, morton_order  # noqa: F401

@@ -1,0 +1,147 @@
+"""Graph models that produce the inputs of the BASELINE configurations.
+
+Each class builds an adjacency ``W`` and hands it to :class:`Graph`; what they
+generate follows the reference generators (file:line cited per class) but the
+construction is vectorised -- the reference's per-vertex Python loops
+(nngraph.py:221-226) make it unusable beyond ~1e6 vertices.  They are input
+fabrication for the filtering path, not part of the timed hot path.
+"""
+import os
+
+import numpy as np
+from scipy import sparse, spatial
+
+from .. import utils
+from .graph import Graph
+
+_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+
+
+def morton_order(coords, bits=None):
+    """Permutation that sorts points along a Z-order (Morton) curve.
+
+    Vertex ids that are close in memory are then close in space, which is what
+    makes the neighbour gather of the SpMM hit L1/L2 (SURVEY.md section 7,
+    "gather locality").  Works for 2-D and 3-D coordinates.
+    """
+    coords = np.asarray(coords, dtype=np.float64)
+    n, d = coords.shape
+    if bits is None:
+        bits = 21 if d <= 3 else 64 // d
+    lo = coords.min(axis=0)
+    span = np.maximum(coords.max(axis=0) - lo, 1e-300)
+    q = np.minimum(((coords - lo) / span * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+    code = np.zeros(n, dtype=np.uint64)
+    for b in range(bits):
+        for k in range(d):
+            code |= ((q[:, k] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * d + k)
+    return np.argsort(code, kind="stable")
+
+
+class Logo(Graph):
+    r"""GSP logo graph, N = 1130 (pygsp/graphs/logo.py:21-33).
+
+    The adjacency and coordinates are the ones of the reference's
+    ``data/pointclouds/logogsp.mat``, stored as ``pygsp_b200/data/logo.npz``.
+    """
+
+    def __init__(self, **kwargs):
+        z = np.load(os.path.join(_DATA, "logo.npz"))
+        n = len(z["indptr"]) - 1
+        W = sparse.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+        self.info = {k: z[k] for k in ("idx_g", "idx_s", "idx_p")}
+        plotting = {"limits": np.array([0, 640, -400, 0])}
+        super().__init__(W, coords=z["coords"], plotting=plotting, **kwargs)
+
+
+class Ring(Graph):
+    r"""Ring graph: vertex i is linked to i +- 1..k (pygsp/graphs/ring.py)."""
+
+    def __init__(self, N=64, k=1, **kwargs):
+        if N < 3:
+            raise ValueError("There should be at least 3 vertices.")
+        if 2 * k > N:
+            raise ValueError("Too many neighbors requested.")
+        self.k = k
+        rows, cols = [], []
+        idx = np.arange(N)
+        for s in range(1, k + 1):
+            rows.append(idx)
+            cols.append((idx + s) % N)
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        W = sparse.coo_matrix((np.ones(rows.size), (rows, cols)), shape=(N, N)).tocsr()
+        W = W + W.T
+        W.data[:] = 1.0                             # unit weights (antipodal edge met twice)
+        theta = 2 * np.pi * idx / N
+        super().__init__(W, coords=np.stack([np.cos(theta), np.sin(theta)], axis=1), **kwargs)
+
+
+class Grid2d(Graph):
+    r"""N1 x N2 grid with 4-neighbour (5-point stencil) connectivity, unit weights.
+
+    Same graph and row-major vertex numbering as pygsp/graphs/grid2d.py:40-89.
+    """
+
+    def __init__(self, N1=16, N2=None, **kwargs):
+        if N2 is None:
+            N2 = N1
+        self.N1, self.N2 = N1, N2
+        N = N1 * N2
+        right = np.ones(N - 1)
+        right[N2 - 1::N2] = 0                       # no edge across a row end
+        W = sparse.diags([right, np.ones(N - N2)], [1, N2], shape=(N, N), format="csr")
+        W.eliminate_zeros()
+        W = (W + W.T).tocsr()
+        x = np.tile(np.arange(N2) / float(N2), N1)
+        y = np.repeat(np.arange(N1)[::-1] / float(N1), N2)
+        super().__init__(W, coords=np.stack([x, y], axis=1), **kwargs)
+
+
+class NNGraph(Graph):
+    r"""k-nearest-neighbour graph of a point cloud with Gaussian weights.
+
+    ``w_ij = exp(-d_ij^2 / sigma)`` for the k nearest neighbours j of i, sigma =
+    mean neighbour distance, then ``W <- (W + W^T)/2`` -- the 'knn' branch of
+    pygsp/graphs/nngraphs/nngraph.py:147-226,289-297 with its default
+    ``center`` / ``rescale`` preprocessing (:127-136).
+    """
+
+    def __init__(self, Xin, k=10, sigma=None, center=True, rescale=True, order=None, **kwargs):
+        Xin = np.asarray(Xin, dtype=np.float64)
+        N, d = Xin.shape
+        if k >= N:
+            raise ValueError("The number of neighbors (k={}) must be smaller than the number "
+                             "of nodes ({}).".format(k, N))
+        X = Xin - Xin.mean(axis=0) if center else Xin.copy()
+        if rescale:
+            radius = 0.5 * np.linalg.norm(X.max(axis=0) - X.min(axis=0), 2)
+            X *= (np.power(N, 1.0 / float(min(d, 3))) / 10.0) / radius
+        if order == "morton":
+            X = X[morton_order(X)]
+        elif order is not None:
+            X = X[np.asarray(order)]
+        D, NN = spatial.cKDTree(X).query(X, k=k + 1, workers=-1)
+        if sigma is None:
+            sigma = np.mean(D[:, 1:])
+        self.k, self.sigma = k, sigma
+        rows = np.repeat(np.arange(N), k)
+        W = sparse.csr_matrix((np.exp(-D[:, 1:].ravel() ** 2 / float(sigma)),
+                               (rows, NN[:, 1:].ravel())), shape=(N, N))
+        W = utils.symmetrize(W, "average").tocsr()
+        super().__init__(W, coords=X, **kwargs)
+
+
+class Sensor(NNGraph):
+    r"""Random sensor network: N uniform points in the unit square, k-NN graph.
+
+    pygsp/graphs/nngraphs/sensor.py:50-75 (non-distributed variant):
+    ``coords = default_rng(seed).uniform(0, 1, (N, 2))``, ``NNGraph(k=k,
+    rescale=False, center=False)``.  ``order='morton'`` renumbers the vertices
+    along a Z-curve (an isomorphic graph with gather-friendly numbering).
+    """
+
+    def __init__(self, N=64, k=6, seed=None, order=None, **kwargs):
+        self.seed = seed
+        coords = np.random.default_rng(seed).uniform(0, 1, (N, 2))
+        kwargs.setdefault("plotting", {"limits": np.array([0, 1, 0, 1])})
+        super().__init__(coords, k=k, center=False, rescale=False, order=order, **kwargs)
