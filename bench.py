@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the Chebyshev filtering hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric  = cheby_op filtered-vertices/sec = N * Nsig * order / t
+workload (N=1): BASELINE configs[1] -- Sensor-type 2-D k-NN graph, N = 1e6, k = 10,
+          seed 0 (Morton-numbered), 64 float32 signals, Heat(scale=50), order 30.
+A "step" is one complete cheby_op call (order fused recurrence kernels).
+
+value   : CUDA-event time of K calls with graph + signals resident in HBM.
+e2e     : the same metric through Filter.filter() with HOST (pinned) signals --
+          H2D and D2H copies inside the timed region.
+roofline: algorithmic bytes of the recurrence / measured kernel time vs the
+          measured HBM copy bandwidth (MEASURED_PEAKS.json).
+cpu_baseline: the oracle port of the reference's scipy path on a bounded sample.
+--impl reference: the reference's CPU path (oracle port; the reference itself is
+          Python and cannot travel to the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cheby_op_filtered_vertices_per_sec"
+UNIT = "vertex*signal*order/s"
+WORKLOAD = dict(name="sensor_knn2d_N1e6_k10_seed0_morton_heat50_order30_nsig64",
+                N=1_000_000, k=10, seed=0, nsig=64, order=30, scale=50.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=None, help="override vertex count (debug)")
+    ap.add_argument("--cpu-columns", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ workload
+def host_graph(n, k, seed):
+    """Adjacency of Sensor(N, k, seed) with Morton vertex numbering, built on the
+    host with scipy's cKDTree (input fabrication, outside every timed region)."""
+    from scipy import sparse, spatial
+    from pygsp_b200.graphs import morton_order
+    coords = np.random.default_rng(seed).uniform(0, 1, (n, 2))
+    coords = coords[morton_order(coords)]
+    D, NN = spatial.cKDTree(coords).query(coords, k=k + 1, workers=-1)
+    sigma = np.mean(D[:, 1:])
+    W = sparse.csr_matrix((np.exp(-D[:, 1:].ravel() ** 2 / sigma),
+                           (np.repeat(np.arange(n), k), NN[:, 1:].ravel())), shape=(n, n))
+    W = ((W + W.T) / 2).tocsr()
+    W.sort_indices()
+    return W
+
+
+def algorithmic_bytes(n, nnz, nsig, nscales, order, itemsize=4):
+    """compulsory traffic of the reference algorithm."""
+    first = (4 + itemsize) * nnz + 4 * (n + 1) + itemsize * n * nsig * (2 + nscales)
+    step = (4 + itemsize) * nnz + 4 * (n + 1) + itemsize * n * nsig * (3 + 2 * nscales)
+    return first, step, first + (order - 1) * step
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
+
+
+# -------------------------------------------------------------- CPU reference
+def _cpu_worker(args):
+    Lparts, lmax, c, x = args
+    from scipy import sparse
+    from oracle import pygsp_oracle as orc
+    L = sparse.csr_matrix(Lparts[:3], shape=Lparts[3])
+    t0 = time.perf_counter()
+    orc.cheby_op(L, lmax, c, x)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_time(L, lmax, c, x, procs):
+    """Wall time of the oracle port (scipy csr_matvecs + numpy, float64 -- the
+    reference's arithmetic) on `x`, signal columns sharded over `procs` processes."""
+    from oracle import pygsp_oracle as orc
+    if procs <= 1:
+        t0 = time.perf_counter()
+        orc.cheby_op(L, lmax, c, x)
+        return time.perf_counter() - t0
+    import multiprocessing as mp
+    parts = (L.data, L.indices, L.indptr, L.shape)
+    chunks = [np.ascontiguousarray(a) for a in np.array_split(x, procs, axis=1) if a.shape[1]]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(chunks)) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(parts, lmax, c, ch) for ch in chunks])
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pygsp_oracle as orc
+    wl = dict(WORKLOAD)
+    if args.n:
+        wl["N"] = args.n
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64)
+    W = host_graph(wl["N"], wl["k"], wl["seed"])
+    L = orc.laplacian(W)
+    lmax = orc.upper_bound(W)                  # estimate_lmax(method="bounds"): deterministic
+    c = orc.cheby_coeff(orc.heat_kernels(lmax, wl["scale"]), lmax, wl["order"])
+    ncols = procs                               # bounded sample: one signal column per process
+    x = np.random.default_rng(0).standard_normal((wl["N"], ncols))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_time(L, lmax, c, x, procs)
+    times = [cpu_reference_time(L, lmax, c, x, procs) for _ in range(args.steps)]
+    t = float(np.sum(times))
+    value = wl["N"] * ncols * wl["order"] * args.steps / t
+    sample = "%d of %d signal columns per step (one per process), full graph, full order" % (
+        ncols, wl["nsig"])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": wl["name"], **{k: wl[k] for k in
+                                        ("N", "k", "nsig", "order")}, "nnz_L": int(L.nnz)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pygsp_b200 as gsp
+    from pygsp_b200.filters import approximations as apx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = dict(WORKLOAD)
+    if args.n:
+        wl["N"] = args.n
+    n, nsig, order = wl["N"], wl["nsig"], wl["order"]
+
+    # ---- build the workload (untimed): graph -> device Laplacian -> device lmax
+    W = host_graph(n, wl["k"], wl["seed"] + rank)      # weak scaling: one graph per rank
+    G = gsp.graphs.Graph(W)
+    G.estimate_lmax()
+    heat = gsp.filters.Heat(G, scale=wl["scale"])
+    c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
+    L = G.L
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    x = torch.randn(n, nsig, device="cuda", generator=gen)
+    lib = gsp._native.lib()
+    lib.gsp_launch_count.restype = __import__("ctypes").c_uint64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for _ in range(max(args.warmup, 3)):
+        apx.cheby_op_device(L, G.lmax, c, x)
+    barrier()
+    launches0 = lib.gsp_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            apx.cheby_op_device(L, G.lmax, c, x)
+        stop.record()
+        barrier()
+    launches = int(lib.gsp_launch_count() - launches0)
+    t_dev = start.elapsed_time(stop) / 1e3
+    t_all = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_dev = float(t_all.item())
+    value = world * n * nsig * order * args.steps / t_dev
+
+    # ---- end to end through the public API with host buffers
+    xh = torch.empty((n, nsig), dtype=torch.float32).pin_memory()
+    xh.copy_(x)
+    for _ in range(2):
+        yh = heat.filter(xh, order=order)
+    barrier()
+    t0 = time.perf_counter()
+    start.record()
+    for _ in range(args.steps):
+        yh = heat.filter(xh, order=order)
+    stop.record()
+    barrier()
+    t_e2e = max(start.elapsed_time(stop) / 1e3, 0.0)
+    t_wall = time.perf_counter() - t0
+    t_e2e = max(t_e2e, t_wall)       # D2H into pinned memory ends on the host side
+    t_all = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_all.item())
+    e2e_value = world * n * nsig * order * args.steps / t_e2e
+    assert tuple(yh.shape) == (n, nsig) and not yh.is_cuda
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (cheby_step_rowgroup, k >= 2)
+    b_first, b_step, b_call = algorithmic_bytes(n, L.nnz, nsig, 1, order)
+    peak, peak_src = measured_peak()
+    achieved = b_call * args.steps / (t_dev if world == 1 else t_dev) / 1e9
+    t_launch = t_dev / args.steps * (b_step / b_call)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(),
+                "kernel": "cheby_step_rowgroup<float,4,16>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_step, "avg_launch_ms": 1e3 * t_launch,
+                "timing": "CUDA events on the launching stream over the timed region"}
+
+    # ---- CPU baseline (oracle port of the scipy path) on a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pygsp_oracle as orc
+        cols = args.cpu_columns
+        Lh = L.to_scipy().astype(np.float64)
+        xs = x[:, :cols].double().cpu().numpy()
+        t_cpu = cpu_reference_time(Lh, G.lmax, c, xs, 1)
+        ref = orc.cheby_op(Lh, G.lmax, c, xs[:, :1])
+        got = apx.cheby_op_device(L, G.lmax, c, x[:, :1].contiguous())[0].cpu().numpy()
+        parity = float(np.abs(got - ref).max() / np.abs(ref).max())
+        cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+               "host_cores_available": os.cpu_count(),
+               "sample": "%d of %d signal columns, full graph, full order, float64 scipy "
+                         "csr_matvecs + numpy (oracle port), best of 1" % (cols, nsig),
+               "parity_rel_err_vs_gpu": parity}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": wl["name"], "N": n, "k": wl["k"], "nsig": nsig, "order": order,
+                      "nnz_L": int(L.nnz), "lmax": G.lmax, "per_gpu": "one graph per rank",
+                      "l2_policy": "inputs_exceed_l2 (working set %.2f GB per call >> 126 MB)"
+                                   % ((4 * n * nsig * 4 + 8 * L.nnz) / 1e9)},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * nsig,
+                   "d2h_bytes_per_step": 4 * n * nsig, "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "api": "pygsp_b200.filters.Heat(G, 50).filter(pinned_host_tensor, order=30)"},
+           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "clocks": clocks.summary()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

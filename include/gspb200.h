@@ -30,6 +30,8 @@ extern "C" {
 
 int gsp_abi_version(void);
 const char* gsp_last_error(void);
+/* number of kernels this library has launched since it was loaded */
+uint64_t gsp_launch_count(void);
 int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
 
 /* ------------------------------------------------------------------ filter --
@@ -71,7 +73,7 @@ int gsp_spmm_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const
 /* ------------------------------------------------------------------- lmax ---
  * gsp_lanczos_*: pygsp/graphs/graph.py:911-917 (scipy eigsh -> ARPACK).
  *   Runs Lanczos iterations [j0, j1) on L.  V3 holds 3*n elements, scal_dev
- *   2*cap+1 doubles: alpha[0..cap) | beta[0..cap) | scratch.  j0 == 0 seeds the
+ *   2*cap+4096 doubles: alpha[0..cap) | beta[0..cap) | reduction partials.  j0 == 0 seeds the
  *   start vector from `seed` (counter-based, reproducible).  The host reads
  *   alpha/beta back and diagonalises the tridiagonal matrix.
  */

@@ -21,6 +21,9 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
   return code;
 }
 
+// kernels launched by this library since load (bench.py's gpu_launches)
+void note_launch(int n);
+
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return GSP_OK;
   return fail(GSP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -34,6 +37,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 #define GSP_LAUNCH_CHECK(name)                                \
   do {                                                        \
+    gsp::note_launch(1);                                      \
     int _rc = gsp::check_cuda(cudaGetLastError(), name);      \
     if (_rc != GSP_OK) return _rc;                            \
   } while (0)

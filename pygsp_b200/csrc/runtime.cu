@@ -9,6 +9,10 @@ char* error_buffer() {
   return buf;
 }
 
+static unsigned long long g_launches = 0;
+void note_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -29,6 +33,8 @@ extern "C" {
 int gsp_abi_version(void) { return GSPB200_ABI_VERSION; }
 
 const char* gsp_last_error(void) { return gsp::error_buffer(); }
+
+uint64_t gsp_launch_count(void) { return gsp::launches(); }
 
 int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
   int dev = 0;

@@ -1,0 +1,73 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the
+header declares; host-side logic that needs no GPU."""
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol():
+    from pygsp_b200 import _native
+    lib = _native.lib()
+    names = _native.header_symbols()
+    assert len(names) >= 36
+    for required in ("gsp_cheby_op_f32", "gsp_cheby_step_f64", "gsp_laplacian_fill_f32",
+                     "gsp_lanczos_f32", "gsp_spectral_bounds_f64", "gsp_launch_count"):
+        assert required in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.gsp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pygsp_b200 as gsp
+    with pytest.raises(gsp._native.NativeError):
+        gsp.graphs.Graph(np.ones((3, 3)) - np.eye(3))
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pygsp_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_cheby_coefficients_host(golden):
+    """compute_cheby_coeff is host code: check it against the PyGSP goldens."""
+    from pygsp_b200 import filters
+
+    class FakeGraph:
+        lmax = float(golden("sensor123")["lmax"])
+        N = 123
+
+    g = golden("sensor123")
+    G = FakeGraph()
+    np.testing.assert_allclose(filters.compute_cheby_coeff(filters.Heat(G), m=30),
+                               g["heat10_coeff"], rtol=1e-10, atol=1e-14)
+    c = filters.compute_cheby_coeff(filters.MexicanHat(G, Nf=5), m=40)
+    assert isinstance(c, list) and len(c) == 5
+    np.testing.assert_allclose(np.array(c), g["mh5_coeff"], rtol=1e-10, atol=1e-13)
+    c = filters.compute_cheby_coeff(filters.Heat(G, scale=[8, 9]), m=30, i=1)
+    np.testing.assert_allclose(c, g["heat89_coeff"][1], rtol=1e-10, atol=1e-14)
+    f = filters.MexicanHat(G, Nf=5)
+    assert f.Nf == 5 and len(f) == 5 and f.shape == (5, 1)
+    assert f.evaluate(np.linspace(0, G.lmax, 11)).shape == (5, 11)
+    assert "MexicanHat(in=1, out=5" in repr(f)
+    with pytest.raises(ValueError):
+        filters.MexicanHat(G, Nf=5, scales=[1, 2])
+
+
+def test_morton_order_is_a_permutation():
+    from pygsp_b200.graphs import morton_order
+    pts = np.random.default_rng(0).uniform(size=(1000, 2))
+    perm = morton_order(pts)
+    assert sorted(perm.tolist()) == list(range(1000))
+    # neighbours in the order are close in space (vs ~0.52 for a random order)
+    d = np.linalg.norm(np.diff(pts[perm], axis=0), axis=1).mean()
+    assert d < 0.1
+    assert sorted(morton_order(np.random.default_rng(1).uniform(size=(500, 3))).tolist()) == list(range(500))

@@ -166,3 +166,17 @@ def test_grid_bank(golden):
     np.testing.assert_allclose(orc.cheby_coeff(mh, lmax, 50), g["coeff"], rtol=1e-10, atol=1e-13)
     y = orc.filter_signal(L, lmax, mh, g["signal"], order=50)
     assert relerr_cols(y, g["filtered"]) < 1e-11
+
+
+def test_c_oracle_matches(golden):
+    """oracle/cheby_oracle.c (plain C restatement) == numpy oracle == PyGSP goldens."""
+    from oracle import build_oracle
+    g = golden("sensor123")
+    L = csr_from(g, "s_Lc")
+    lmax = float(g["lmax"])
+    y = build_oracle.cheby_op(L, lmax, g["mh5_coeff"], g["mh5_block"])
+    np.testing.assert_allclose(y, g["mh5_cheby_op"], rtol=1e-10, atol=1e-12)
+    y1 = build_oracle.cheby_op(L, lmax, g["heat10_coeff"], g["signal"])
+    np.testing.assert_allclose(y1, g["heat10_cheb"], rtol=1e-11, atol=1e-14)
+    with pytest.raises(TypeError):
+        build_oracle.cheby_op(L, lmax, [1.0], g["signal"])
