@@ -41,6 +41,7 @@ int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
  *   reference's TypeError condition is reported as -1); x is (n, nsig)
  *   row-major; r receives (nscales, n, nsig) = the reference's filter-major
  *   (nscales*n, nsig) block; work holds 2*n*nsig elements.  x is not modified.
+ *   nnz = number of stored entries of L; plan_host may be NULL (row-group kernel).
  * gsp_cheby_step_*: one fused recurrence step on rows [row_begin, row_end)
  *   x_new = alpha*(L x_cur) + beta*x_cur + gamma*x_old ;  r_i (+)= ck[i]*x_new
  *   (first != 0: r_i = c0[i]/2 * x_cur + ck[i] * x_new, x_old unused).
@@ -49,26 +50,38 @@ int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
  *   where column indices address a local x_cur that has halo rows appended.
  * gsp_spmm_*: y = L x, scipy `csr_matrix.dot` (approximations.py:99, graph.py:955).
  */
-int gsp_cheby_op_f32(int64_t n, const int32_t* indptr, const int32_t* indices,
-                     const float* data, double lmax, const double* coeffs_host, int nscales,
-                     int m, const float* x, int64_t nsig, float* r, float* work, void* stream);
-int gsp_cheby_op_f64(int64_t n, const int32_t* indptr, const int32_t* indices,
-                     const double* data, double lmax, const double* coeffs_host, int nscales,
-                     int m, const double* x, int64_t nsig, double* r, double* work, void* stream);
-int gsp_cheby_step_f32(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
-                       const int32_t* indices, const float* data, const float* x_cur,
-                       const float* x_old, float* x_new, float* r, int64_t r_rows,
-                       int64_t nsig, int nscales, const double* ck_host, const double* c0_host,
-                       double alpha, double beta, double gamma, void* stream);
-int gsp_cheby_step_f64(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
-                       const int32_t* indices, const double* data, const double* x_cur,
-                       const double* x_old, double* x_new, double* r, int64_t r_rows,
-                       int64_t nsig, int nscales, const double* ck_host, const double* c0_host,
-                       double alpha, double beta, double gamma, void* stream);
-int gsp_spmm_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
-                 const float* x, int64_t nsig, float* y, void* stream);
-int gsp_spmm_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                 const double* x, int64_t nsig, double* y, void* stream);
+/* Tiling of the float32 fast path (TMA-staged row tiles, csrc/cheby_tiled.cu).
+ * Filled by gsp_cheby_tile_plan() once per (matrix, nsig, nscales); all zeros
+ * means "use the row-group kernel".  Plain host struct, owned by the caller. */
+typedef struct gsp_tile_plan {
+  int rows_per_tile;   /* rows of L per shared-memory stage */
+  int slab_capacity;   /* CSR entries a stage can hold (>= the matrix's largest tile) */
+  int stages;          /* depth of the TMA ring */
+  int consumer_warps;  /* warps that compute (one more warp produces) */
+  int gather_unroll;   /* neighbour packets requested back to back */
+  int blocks_per_sm;   /* 0 = as many as fit */
+} gsp_tile_plan;
+
+/* Reads the matrix's largest tile (synchronises `stream` once) and chooses the tiling. */
+int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales,
+                        gsp_tile_plan* plan_host_out, void* stream);
+
+#define GSPB200_DECLARE_CHEBY_API(SUF, T)                                                         \
+  int gsp_cheby_op_##SUF(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,   \
+                         const T* data, double lmax, const double* coeffs_host, int nscales,      \
+                         int m, const T* x, int64_t nsig, T* r, T* work,                          \
+                         const gsp_tile_plan* plan_host, void* stream);                           \
+  int gsp_cheby_step_##SUF(int first, int64_t row_begin, int64_t row_end, int64_t nnz,            \
+                           const int32_t* indptr, const int32_t* indices, const T* data,          \
+                           const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,        \
+                           int64_t nsig, int nscales, const double* ck_host,                      \
+                           const double* c0_host, double alpha, double beta, double gamma,        \
+                           const gsp_tile_plan* plan_host, void* stream);                         \
+  int gsp_spmm_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data,     \
+                     const T* x, int64_t nsig, T* y, void* stream);
+
+GSPB200_DECLARE_CHEBY_API(f32, float)
+GSPB200_DECLARE_CHEBY_API(f64, double)
 
 /* ------------------------------------------------------------------- lmax ---
  * gsp_lanczos_*: pygsp/graphs/graph.py:911-917 (scipy eigsh -> ARPACK).

@@ -20,13 +20,24 @@ class NativeError(RuntimeError):
     pass
 
 
+class TilePlan(ctypes.Structure):
+    """Mirror of ``gsp_tile_plan`` (include/gspb200.h)."""
+    _fields_ = [("rows_per_tile", ctypes.c_int), ("slab_capacity", ctypes.c_int),
+                ("stages", ctypes.c_int), ("consumer_warps", ctypes.c_int),
+                ("gather_unroll", ctypes.c_int), ("blocks_per_sm", ctypes.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def header_symbols():
     """Every function name include/gspb200.h declares (macro-expanded)."""
     text = open(_HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    macro = re.search(r"#define GSPB200_DECLARE_GRAPH_API\(SUF, T\)(.*?)\n\n", text, flags=re.S)
-    templ = re.findall(r"\b(gsp_[a-z0-9_]+_)##SUF", macro.group(1)) if macro else []
-    body = text.replace(macro.group(0), "") if macro else text
+    templ, body = [], text
+    for macro in re.finditer(r"#define GSPB200_DECLARE_[A-Z]+_API\(SUF, T\)(.*?)\n\n", text, flags=re.S):
+        templ += re.findall(r"\b(gsp_[a-z0-9_]+_)##SUF", macro.group(1))
+        body = body.replace(macro.group(0), "")
     out = set(re.findall(r"\b(gsp_[a-z0-9_]+)\s*\(", body))
     for t in templ:
         out.add(t + "f32")
@@ -56,6 +67,8 @@ def _arg(a):
     """torch tensor -> device pointer; None -> NULL; numpy -> host pointer."""
     if a is None:
         return ctypes.c_void_p(0)
+    if isinstance(a, TilePlan):
+        return ctypes.byref(a)
     if hasattr(a, "data_ptr"):
         return ctypes.c_void_p(a.data_ptr())
     if isinstance(a, np.ndarray):

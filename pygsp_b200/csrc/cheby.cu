@@ -26,6 +26,15 @@
 
 namespace gsp {
 
+int cheby_step_tiled_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+                         const int32_t* indices, const float* vals, const float* x_cur,
+                         const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
+                         int nscales, const double* ck, const double* c0, double alpha, double beta,
+                         double gamma, const gsp_tile_plan& plan, int64_t* rows_done,
+                         cudaStream_t st);
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 constexpr int kMaxScales = 16;   // coefficients per launch passed by value
 constexpr int kStepThreads = 256;
 
@@ -186,7 +195,6 @@ template <typename T> struct MaxVec;
 template <> struct MaxVec<float> { static constexpr int value = 4; };
 template <> struct MaxVec<double> { static constexpr int value = 2; };
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // One recurrence step over rows [rb, re).  Handles any nsig / nscales.
 template <typename T>
@@ -233,11 +241,46 @@ int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
   return GSP_OK;
 }
 
+template <typename T>
+static int cheby_step_planned(const gsp_tile_plan* plan, int64_t nnz, bool first, int64_t rb,
+                              int64_t re, const int32_t* indptr, const int32_t* indices,
+                              const T* vals, const T* x_cur, const T* x_old, T* x_new, T* r,
+                              int64_t r_rows, int nsig, int nscales, const double* ck,
+                              const double* c0, double alpha, double beta, double gamma,
+                              cudaStream_t st) {
+  return cheby_step<T>(first, rb, re, indptr, indices, vals, x_cur, x_old, x_new, r, r_rows, nsig,
+                       nscales, ck, c0, alpha, beta, gamma, st);
+}
+
+// float32 with a tile plan: TMA-tiled kernel on the full tiles of [0, re), the
+// row-group kernel on the remaining (< rows_per_tile) rows.
+template <>
+int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first, int64_t rb,
+                              int64_t re, const int32_t* indptr, const int32_t* indices,
+                              const float* vals, const float* x_cur, const float* x_old,
+                              float* x_new, float* r, int64_t r_rows, int nsig, int nscales,
+                              const double* ck, const double* c0, double alpha, double beta,
+                              double gamma, cudaStream_t st) {
+  const bool tiled = plan && plan->rows_per_tile > 0 && rb == 0 && nscales <= kMaxScales &&
+                     aligned16(indptr) && aligned16(indices) && aligned16(vals) &&
+                     aligned16(x_cur) && aligned16(x_new) && aligned16(r) &&
+                     (first || aligned16(x_old));
+  int64_t done = 0;
+  if (tiled) {
+    int rc = cheby_step_tiled_f32(first, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
+                                  r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, &done,
+                                  st);
+    if (rc != GSP_OK) return rc;
+  }
+  return cheby_step<float>(first, rb + done, re, indptr, indices, vals, x_cur, x_old, x_new, r,
+                           r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st);
+}
+
 // Full operator (approximations.py:58-114): K = m-1 fused steps on `stream`.
 template <typename T>
-int cheby_op(int64_t n, const int32_t* indptr, const int32_t* indices, const T* vals,
-             double lmax, const double* coeffs, int nscales, int m, const T* x, int nsig,
-             T* r, T* work, cudaStream_t st) {
+int cheby_op(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+             const T* vals, double lmax, const double* coeffs, int nscales, int m, const T* x,
+             int nsig, T* r, T* work, const gsp_tile_plan* plan, cudaStream_t st) {
   GSP_REQUIRE(n >= 0 && nsig >= 1 && nscales >= 1, "bad sizes");
   GSP_REQUIRE(m >= 2, "The coefficients have an invalid shape");   // approximations.py:83-84
   GSP_REQUIRE(lmax > 0 && lmax == lmax, "lmax must be positive");
@@ -255,15 +298,15 @@ int cheby_op(int64_t n, const int32_t* indptr, const int32_t* indices, const T* 
     int rc;
     if (k == 1) {
       // T_1 = (L x - a x)/a = (2/lmax) L x - x ; r_i = c_i0/2 T_0 + c_i1 T_1
-      rc = cheby_step<T>(true, 0, n, indptr, indices, vals, x, nullptr, buf[0], r, n, nsig,
-                         nscales, ck, c0, 2.0 / lmax, -1.0, 0.0, st);
+      rc = cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, x, nullptr, buf[0],
+                                 r, n, nsig, nscales, ck, c0, 2.0 / lmax, -1.0, 0.0, st);
       t_cur = buf[0];
     } else {
       // T_k = (4/lmax) L T_{k-1} - 2 T_{k-1} - T_{k-2}, written over T_{k-2}
       // (row-local) except for k == 2 where T_0 is the caller's input.
       T* dst = (k == 2) ? buf[1] : const_cast<T*>(t_old);
-      rc = cheby_step<T>(false, 0, n, indptr, indices, vals, t_cur, t_old, dst, r, n, nsig,
-                         nscales, ck, c0, 4.0 / lmax, -2.0, -1.0, st);
+      rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, t_cur, t_old, dst,
+                                 r, n, nsig, nscales, ck, c0, 4.0 / lmax, -2.0, -1.0, st);
       t_old = t_cur;
       t_cur = dst;
     }
@@ -297,55 +340,34 @@ template int cheby_step<double>(bool, int64_t, int64_t, const int32_t*, const in
 // ------------------------------- C ABI ------------------------------------
 extern "C" {
 
-int gsp_cheby_op_f32(int64_t n, const int32_t* indptr, const int32_t* indices,
-                     const float* data, double lmax, const double* coeffs_host, int nscales,
-                     int m, const float* x, int64_t nsig, float* r, float* work, void* stream) {
-  GSP_REQUIRE(nsig <= (1 << 20), "nsig too large");
-  return gsp::cheby_op<float>(n, indptr, indices, data, lmax, coeffs_host, nscales, m, x,
-                              (int)nsig, r, work, gsp::as_stream(stream));
-}
+#define GSP_CHEBY_API(SUF, T)                                                                     \
+  int gsp_cheby_op_##SUF(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,   \
+                         const T* data, double lmax, const double* coeffs_host, int nscales,      \
+                         int m, const T* x, int64_t nsig, T* r, T* work,                          \
+                         const gsp_tile_plan* plan_host, void* stream) {                          \
+    GSP_REQUIRE(nsig >= 1 && nsig <= (1 << 20), "nsig out of range");                             \
+    return gsp::cheby_op<T>(n, nnz, indptr, indices, data, lmax, coeffs_host, nscales, m, x,      \
+                            (int)nsig, r, work, plan_host, gsp::as_stream(stream));               \
+  }                                                                                               \
+  int gsp_cheby_step_##SUF(int first, int64_t row_begin, int64_t row_end, int64_t nnz,            \
+                           const int32_t* indptr, const int32_t* indices, const T* data,          \
+                           const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,        \
+                           int64_t nsig, int nscales, const double* ck_host,                      \
+                           const double* c0_host, double alpha, double beta, double gamma,        \
+                           const gsp_tile_plan* plan_host, void* stream) {                        \
+    GSP_REQUIRE(nsig >= 1 && nsig <= (1 << 20), "nsig out of range");                             \
+    return gsp::cheby_step_planned<T>(plan_host, nnz, first != 0, row_begin, row_end, indptr,     \
+                                      indices, data, x_cur, x_old, x_new, r, r_rows, (int)nsig,   \
+                                      nscales, ck_host, c0_host, alpha, beta, gamma,              \
+                                      gsp::as_stream(stream));                                    \
+  }                                                                                               \
+  int gsp_spmm_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data,     \
+                     const T* x, int64_t nsig, T* y, void* stream) {                              \
+    GSP_REQUIRE(nsig >= 1 && nsig <= (1 << 20), "nsig out of range");                             \
+    return gsp::spmm_plain<T>(n, indptr, indices, data, x, (int)nsig, y, gsp::as_stream(stream)); \
+  }
 
-int gsp_cheby_op_f64(int64_t n, const int32_t* indptr, const int32_t* indices,
-                     const double* data, double lmax, const double* coeffs_host, int nscales,
-                     int m, const double* x, int64_t nsig, double* r, double* work,
-                     void* stream) {
-  GSP_REQUIRE(nsig <= (1 << 20), "nsig too large");
-  return gsp::cheby_op<double>(n, indptr, indices, data, lmax, coeffs_host, nscales, m, x,
-                               (int)nsig, r, work, gsp::as_stream(stream));
-}
-
-int gsp_cheby_step_f32(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
-                       const int32_t* indices, const float* data, const float* x_cur,
-                       const float* x_old, float* x_new, float* r, int64_t r_rows,
-                       int64_t nsig, int nscales, const double* ck_host,
-                       const double* c0_host, double alpha, double beta, double gamma,
-                       void* stream) {
-  return gsp::cheby_step<float>(first != 0, row_begin, row_end, indptr, indices, data, x_cur,
-                                x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host, c0_host,
-                                alpha, beta, gamma, gsp::as_stream(stream));
-}
-
-int gsp_cheby_step_f64(int first, int64_t row_begin, int64_t row_end, const int32_t* indptr,
-                       const int32_t* indices, const double* data, const double* x_cur,
-                       const double* x_old, double* x_new, double* r, int64_t r_rows,
-                       int64_t nsig, int nscales, const double* ck_host,
-                       const double* c0_host, double alpha, double beta, double gamma,
-                       void* stream) {
-  return gsp::cheby_step<double>(first != 0, row_begin, row_end, indptr, indices, data, x_cur,
-                                 x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
-                                 c0_host, alpha, beta, gamma, gsp::as_stream(stream));
-}
-
-int gsp_spmm_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
-                 const float* x, int64_t nsig, float* y, void* stream) {
-  return gsp::spmm_plain<float>(n, indptr, indices, data, x, (int)nsig, y,
-                                gsp::as_stream(stream));
-}
-
-int gsp_spmm_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                 const double* x, int64_t nsig, double* y, void* stream) {
-  return gsp::spmm_plain<double>(n, indptr, indices, data, x, (int)nsig, y,
-                                 gsp::as_stream(stream));
-}
+GSP_CHEBY_API(f32, float)
+GSP_CHEBY_API(f64, double)
 
 }  // extern "C"

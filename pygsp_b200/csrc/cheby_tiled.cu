@@ -1,0 +1,387 @@
+// Tiled, warp-specialised Chebyshev step for sm_100a: the float32 fast path.
+//
+// Same arithmetic as cheby_step_rowgroup (csrc/cheby.cu) -- and therefore the same
+// reference lines, pygsp/filters/approximations.py:99-112 -- but every operand
+// that is read *contiguously* no longer passes through registers/L1:
+//
+//   * a persistent CTA owns row tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   * warp 0 is a producer: for each tile it issues 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) of the tile's CSR slab
+//     (indptr / indices / values) and of the tile's x_old and r rows into a
+//     ring of `stages` shared-memory stages, several tiles ahead;
+//   * the consumer warps wait on the stage's "full" mbarrier, read the CSR
+//     entries from shared memory (broadcast, no shuffles), gather x_cur rows with
+//     coalesced 16-byte loads through L1/L2 (the only traffic left on that path,
+//     so L1 holds nothing but x_cur), accumulate in registers in stored CSR
+//     order, apply the three-term recurrence and the coefficient AXPYs and store
+//     x_new / r with streaming 16-byte stores; then release the stage ("empty").
+//
+// Lane mapping: G = nsig/4 lanes own one row (a float4 packet each), 32/G rows
+// per warp in flight.  A tile's slab must fit `slab_cap` entries: the caller
+// obtains the bound from tile_nnz_max() once per matrix (see gsp_cheby_tile_plan).
+#include "common.cuh"
+#include "gspb200.h"
+
+namespace gsp {
+
+constexpr int kTiledMaxScales = 16;
+
+struct TileArgs {
+  int64_t n_tiles;
+  int64_t r_rows;
+  int64_t nnz;
+  const int32_t* indptr;
+  const int32_t* indices;
+  const float* vals;
+  const float* x_cur;
+  const float* x_old;
+  float* x_new;
+  float* r;
+  int rows_per_tile;   // R, multiple of 4
+  int slab_cap;        // entries per stage for indices / values (multiple of 4)
+  int stages;
+  int consumer_warps;
+  int nsig;
+  int nscales;
+  float alpha, beta, gamma;
+  float half_c0[kTiledMaxScales];
+  float ck[kTiledMaxScales];
+};
+
+// ----------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_addr(dst)),
+      "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void stcs_f4(float* p, const float4& v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+// shared-memory carve-up, identical on host and device
+struct TileLayout {
+  int vec_bytes;      // x_old + r tiles of one stage
+  int slab_bytes;     // one of the two CSR slabs
+  int ptr_bytes;      // indptr slab + trailing slot
+  int stage_bytes;
+  int bar_bytes;
+  __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages) {
+    vec_bytes = first ? 0 : (1 + nscales) * R * nsig * 4;
+    slab_bytes = (cap + 8) * 4;                 // +8: unrolled reads may run past the end
+    ptr_bytes = (R + 4) * 4;
+    stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;
+    bar_bytes = ((2 * stages * 8 + 15) / 16) * 16;
+  }
+  __host__ __device__ int total(int stages) const { return bar_bytes + stages * stage_bytes; }
+};
+
+template <int G, int U, bool FIRST>
+__global__ void __launch_bounds__(32 * 17)
+cheby_step_tiled(const __grid_constant__ TileArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int R = a.rows_per_tile;
+  const int S = a.stages;
+  const int NW = a.consumer_warps;
+  const int nsig = a.nsig;
+  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + S;
+  unsigned char* stage0 = smem + lay.bar_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- producer
+    if (lane != 0) return;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % S;
+      const uint32_t round = uint32_t(it / S);
+      mbar_wait(empty + s, (round & 1u) ^ 1u);      // slot free (passes at once in round 0)
+      unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
+      float* sm_vec = reinterpret_cast<float*>(st);
+      int32_t* sm_col = reinterpret_cast<int32_t*>(st + lay.vec_bytes);
+      float* sm_val = reinterpret_cast<float*>(st + lay.vec_bytes + lay.slab_bytes);
+      int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
+      int32_t* sm_meta = sm_ptr + (R + 4);
+
+      const int64_t r0 = tile * R;
+      const int begin = __ldg(a.indptr + r0);
+      const int end = __ldg(a.indptr + r0 + R);
+      const int a0 = begin & ~3;                    // 16-byte aligned slab start
+      int a1 = (end + 3) & ~3;
+      if (int64_t(a1) > a.nnz) a1 = end & ~3;      // never read past the arrays
+      sm_ptr[R] = end;                              // the bulk copy brings indptr[r0 .. r0+R)
+      sm_meta[0] = a0;
+      for (int k = (a1 > a0 ? a1 : a0); k < end; ++k) {   // <= 3 trailing entries, last tile only
+        sm_col[k - a0] = __ldg(a.indices + k);
+        sm_val[k - a0] = __ldg(a.vals + k);
+      }
+      const uint32_t slab = a1 > a0 ? uint32_t(a1 - a0) * 4u : 0u;
+      const uint32_t tile_vec = uint32_t(R) * nsig * 4u;
+      const uint32_t bytes = uint32_t(R) * 4u + 2u * slab + (FIRST ? 0u : tile_vec * (1 + a.nscales));
+      mbar_expect_tx(full + s, bytes);
+      bulk_g2s(sm_ptr, a.indptr + r0, uint32_t(R) * 4u, full + s);
+      if (slab) {
+        bulk_g2s(sm_col, a.indices + a0, slab, full + s);
+        bulk_g2s(sm_val, a.vals + a0, slab, full + s);
+      }
+      if (!FIRST) {
+        bulk_g2s(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s);
+        for (int i = 0; i < a.nscales; ++i)
+          bulk_g2s(sm_vec + size_t(i + 1) * R * nsig,
+                   a.r + (int64_t(i) * a.r_rows + r0) * nsig, tile_vec, full + s);
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers
+  constexpr int RP = 32 / G;               // rows in flight per warp
+  const int cw = warp - 1;
+  const int sub = lane / G;
+  const int c0 = (lane % G) * 4;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % S;
+    const uint32_t round = uint32_t(it / S);
+    mbar_wait(full + s, round & 1u);
+    const unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
+    const float* sm_vec = reinterpret_cast<const float*>(st);
+    const int32_t* sm_col = reinterpret_cast<const int32_t*>(st + lay.vec_bytes);
+    const float* sm_val = reinterpret_cast<const float*>(st + lay.vec_bytes + lay.slab_bytes);
+    const int32_t* sm_ptr = reinterpret_cast<const int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
+    const int a0 = sm_ptr[R + 4];
+    const int64_t r0 = tile * R;
+
+    for (int lr = cw * RP + sub; lr < R; lr += NW * RP) {
+      const int64_t row = r0 + lr;
+      const int jb = sm_ptr[lr] - a0;
+      const int je = sm_ptr[lr + 1] - a0;
+      const float4 xc = ldg_f4(a.x_cur + row * nsig + c0);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = jb; j < je; j += U) {
+        float4 xv[U];
+        float wv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = j + u < je;
+          const int col = sm_col[j + u];
+          wv[u] = ok ? sm_val[j + u] : 0.f;
+          xv[u] = ok ? ldg_f4(a.x_cur + int64_t(col) * nsig + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc.x = fmaf(wv[u], xv[u].x, acc.x);
+          acc.y = fmaf(wv[u], xv[u].y, acc.y);
+          acc.z = fmaf(wv[u], xv[u].z, acc.z);
+          acc.w = fmaf(wv[u], xv[u].w, acc.w);
+        }
+      }
+      float4 xn;
+      xn.x = fmaf(a.alpha, acc.x, a.beta * xc.x);
+      xn.y = fmaf(a.alpha, acc.y, a.beta * xc.y);
+      xn.z = fmaf(a.alpha, acc.z, a.beta * xc.z);
+      xn.w = fmaf(a.alpha, acc.w, a.beta * xc.w);
+      if (!FIRST) {
+        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + lr * nsig + c0);
+        xn.x = fmaf(a.gamma, xo.x, xn.x);
+        xn.y = fmaf(a.gamma, xo.y, xn.y);
+        xn.z = fmaf(a.gamma, xo.z, xn.z);
+        xn.w = fmaf(a.gamma, xo.w, xn.w);
+      }
+      stcs_f4(a.x_new + row * nsig + c0, xn);
+      for (int i = 0; i < a.nscales; ++i) {
+        float4 rv;
+        if (FIRST) {
+          rv.x = fmaf(a.ck[i], xn.x, a.half_c0[i] * xc.x);
+          rv.y = fmaf(a.ck[i], xn.y, a.half_c0[i] * xc.y);
+          rv.z = fmaf(a.ck[i], xn.z, a.half_c0[i] * xc.z);
+          rv.w = fmaf(a.ck[i], xn.w, a.half_c0[i] * xc.w);
+        } else {
+          rv = *reinterpret_cast<const float4*>(sm_vec + (size_t(i + 1) * R + lr) * nsig + c0);
+          rv.x = fmaf(a.ck[i], xn.x, rv.x);
+          rv.y = fmaf(a.ck[i], xn.y, rv.y);
+          rv.z = fmaf(a.ck[i], xn.z, rv.z);
+          rv.w = fmaf(a.ck[i], xn.w, rv.w);
+        }
+        stcs_f4(a.r + (int64_t(i) * a.r_rows + row) * nsig + c0, rv);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+}
+
+// max over tiles of the 16-byte-aligned CSR slab length of a tile
+__global__ void tile_nnz_max_kernel(int64_t n_tiles, int rows_per_tile,
+                                    const int32_t* __restrict__ indptr, int* out) {
+  int best = 0;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n_tiles;
+       t += int64_t(gridDim.x) * blockDim.x) {
+    const int begin = indptr[t * rows_per_tile] & ~3;
+    const int end = (indptr[(t + 1) * rows_per_tile] + 3) & ~3;
+    best = max(best, end - begin);
+  }
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+}
+
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : fallback;
+}
+
+// Decide the tiling for (matrix, nsig, nscales).  Synchronises `st` once.
+int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_tile_plan* plan,
+              cudaStream_t st) {
+  memset(plan, 0, sizeof(*plan));
+  const char* force = getenv("GSPB200_KERNEL");
+  if (force && strcmp(force, "rowgroup") == 0) return GSP_OK;
+  if (!(nsig == 32 || nsig == 64 || nsig == 128)) return GSP_OK;
+  if (nscales < 0 || nscales > kTiledMaxScales) return GSP_OK;
+  int R = env_int("GSPB200_TILE_R", nscales <= 2 ? 32 : 16);
+  if (nsig == 128) R = std::max(8, R / 2);
+  R = std::max(8, (R / 8) * 8);
+  const int64_t n_tiles = n / R;
+  if (n_tiles < 1) return GSP_OK;
+  int* dmax = nullptr;
+  GSP_CUDA(cudaMallocAsync((void**)&dmax, sizeof(int), st));
+  GSP_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), st));
+  const int blocks = (int)std::min<int64_t>(ceil_div(n_tiles, 256), 1024);
+  tile_nnz_max_kernel<<<blocks, 256, 0, st>>>(n_tiles, R, indptr, dmax);
+  GSP_LAUNCH_CHECK("tile_nnz_max");
+  int hmax = 0;
+  GSP_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GSP_CUDA(cudaStreamSynchronize(st));
+  cudaFreeAsync(dmax, st);
+  const int cap = ((hmax + 8 + 63) / 64) * 64;
+  int stages = env_int("GSPB200_TILE_S", 3);
+  const int warps = std::min(16, std::max(1, env_int("GSPB200_TILE_NW", 16)));
+  // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
+  const int budget = env_int("GSPB200_TILE_SMEM", 100 * 1024);
+  TileLayout lay(R, cap, (int)nsig, nscales, false, stages);
+  while (stages > 2 && lay.total(stages) > budget) { --stages; lay = TileLayout(R, cap, (int)nsig, nscales, false, stages); }
+  if (lay.total(stages) > 200 * 1024) return GSP_OK;        // heavy rows: row-group kernel
+  plan->rows_per_tile = R;
+  plan->slab_capacity = cap;
+  plan->stages = stages;
+  plan->consumer_warps = warps;
+  plan->gather_unroll = env_int("GSPB200_TILE_U", 4);
+  plan->blocks_per_sm = env_int("GSPB200_TILE_BPS", 0);
+  return GSP_OK;
+}
+
+template <int G, int U>
+static int launch_tiled_gu(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
+  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages);
+  const int smem = lay.total(a.stages);
+  const int threads = 32 * (1 + a.consumer_warps);
+  auto kern = first ? cheby_step_tiled<G, U, true> : cheby_step_tiled<G, U, false>;
+  GSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  GSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail(GSP_ERR_UNSUPPORTED, "tiled kernel does not fit (%s)", "smem");
+  if (blocks_per_sm > 0) per_sm = std::min(per_sm, blocks_per_sm);
+  const int64_t grid = std::min<int64_t>(a.n_tiles, int64_t(sm_count()) * per_sm);
+  kern<<<(unsigned)grid, threads, smem, st>>>(a);
+  GSP_LAUNCH_CHECK("cheby_step_tiled");
+  return GSP_OK;
+}
+
+template <int G>
+static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cudaStream_t st) {
+  switch (unroll) {
+    case 1: return launch_tiled_gu<G, 1>(first, a, bps, st);
+    case 2: return launch_tiled_gu<G, 2>(first, a, bps, st);
+    case 8: return launch_tiled_gu<G, 8>(first, a, bps, st);
+    default: return launch_tiled_gu<G, 4>(first, a, bps, st);
+  }
+}
+
+// Rows [0, plan.rows_per_tile * n_tiles) of one step; returns the number of rows done.
+int cheby_step_tiled_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+                         const int32_t* indices, const float* vals, const float* x_cur,
+                         const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
+                         int nscales, const double* ck, const double* c0, double alpha, double beta,
+                         double gamma, const gsp_tile_plan& plan, int64_t* rows_done,
+                         cudaStream_t st) {
+  TileArgs a;
+  a.n_tiles = n / plan.rows_per_tile;
+  *rows_done = a.n_tiles * plan.rows_per_tile;
+  if (a.n_tiles == 0) return GSP_OK;
+  a.r_rows = r_rows;
+  a.nnz = nnz;
+  a.indptr = indptr; a.indices = indices; a.vals = vals;
+  a.x_cur = x_cur; a.x_old = x_old; a.x_new = x_new; a.r = r;
+  a.rows_per_tile = plan.rows_per_tile;
+  a.slab_cap = plan.slab_capacity;
+  a.stages = plan.stages;
+  a.consumer_warps = plan.consumer_warps;
+  a.nsig = nsig;
+  a.nscales = nscales;
+  a.alpha = float(alpha); a.beta = float(beta); a.gamma = float(gamma);
+  for (int i = 0; i < kTiledMaxScales; ++i) {
+    a.ck[i] = i < nscales ? float(ck[i]) : 0.f;
+    a.half_c0[i] = (first && i < nscales) ? float(0.5 * c0[i]) : 0.f;
+  }
+  switch (nsig) {
+    case 32: return launch_tiled_g<8>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
+    case 64: return launch_tiled_g<16>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
+    case 128: return launch_tiled_g<32>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
+  }
+  return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 32, 64 or 128 (%s)", "nsig");
+}
+
+}  // namespace gsp
+
+extern "C" int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales,
+                                   gsp_tile_plan* plan_host_out, void* stream) {
+  GSP_REQUIRE(plan_host_out != nullptr, "plan must not be NULL");
+  return gsp::tile_plan(n, indptr, nsig, nscales, plan_host_out, gsp::as_stream(stream));
+}

@@ -92,10 +92,11 @@ def cheby_op_device(L, lmax, c, x):
     c = np.ascontiguousarray(c)
     r = torch.empty((nscales, n, nsig), dtype=L.dtype, device=L.device)
     work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
+    plan = L.tile_plan(nsig, nscales)
     with torch.cuda.device(L.device):
-        nat.call("gsp_cheby_op_" + nat.suffix(L.dtype), nat.i64(n), L.indptr, L.indices, L.data,
-                 nat.f64(lmax), c, nat.i32(nscales), nat.i32(M), x, nat.i64(nsig), r, work,
-                 nat.stream_ptr(L.device))
+        nat.call("gsp_cheby_op_" + nat.suffix(L.dtype), nat.i64(n), nat.i64(L.nnz), L.indptr,
+                 L.indices, L.data, nat.f64(lmax), c, nat.i32(nscales), nat.i32(M), x,
+                 nat.i64(nsig), r, work, plan, nat.stream_ptr(L.device))
     return r
 
 

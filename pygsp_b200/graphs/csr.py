@@ -17,6 +17,21 @@ class DeviceCSR:
         self.indices = indices
         self.data = data
         self.shape = (int(shape[0]), int(shape[1]))
+        self._plans = {}
+
+    def tile_plan(self, nsig, nscales):
+        """Tiling of the float32 TMA path for this matrix (cached; None = row-group kernel)."""
+        torch = nat.require_cuda()
+        if self.data.dtype != torch.float32:
+            return None
+        key = (int(nsig), int(nscales))
+        if key not in self._plans:
+            plan = nat.TilePlan()
+            with torch.cuda.device(self.device):
+                nat.call("gsp_cheby_tile_plan", nat.i64(self.shape[0]), self.indptr,
+                         nat.i64(nsig), nat.i32(nscales), plan, nat.stream_ptr(self.device))
+            self._plans[key] = plan if plan.rows_per_tile > 0 else None
+        return self._plans[key]
 
     # -- construction ---------------------------------------------------------
     @classmethod

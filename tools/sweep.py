@@ -1,0 +1,80 @@
+"""Kernel-variant sweep on the bench workload (run on the GPU box).
+
+    python tools/sweep.py [--n 1000000] [--steps 5] VAR=VAL,VAR=VAL ...
+
+Each positional argument is one configuration: a comma-separated list of
+GSPB200_* environment overrides (without the prefix), e.g.
+    KERNEL=rowgroup   TILE_R=32,TILE_S=3,TILE_NW=8,TILE_U=4
+Prints ms per cheby_op call and the algorithmic HBM fraction for each.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nsig", type=int, default=64)
+    ap.add_argument("--nscales", type=int, default=1)
+    ap.add_argument("--order", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("configs", nargs="*")
+    a = ap.parse_args()
+    import torch
+    import bench
+    import pygsp_b200 as gsp
+    from pygsp_b200.filters import approximations as apx
+
+    W = bench.host_graph(a.n, 10, 0)
+    G = gsp.graphs.Graph(W)
+    G.estimate_lmax()
+    taus = [50.0 / (i + 1) for i in range(a.nscales)]
+    c = np.atleast_2d(np.array(gsp.filters.compute_cheby_coeff(gsp.filters.Heat(G, taus), m=a.order)))
+    x = torch.randn(a.n, a.nsig, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    _, _, b_call = bench.algorithmic_bytes(a.n, G.L.nnz, a.nsig, a.nscales, a.order)
+    peak, _ = bench.measured_peak()
+    ref = None
+    results = []
+    for cfg in a.configs or ["KERNEL=rowgroup"]:
+        for k in [k for k in os.environ if k.startswith("GSPB200_")]:
+            del os.environ[k]
+        for kv in cfg.split(","):
+            k, v = kv.split("=")
+            os.environ["GSPB200_" + k] = v
+        G.L._plans.clear()
+        try:
+            for _ in range(3):
+                y = apx.cheby_op_device(G.L, G.lmax, c, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                y = apx.cheby_op_device(G.L, G.lmax, c, x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            if ref is None:
+                ref = y.clone()
+            err = float((y - ref).abs().max() / ref.abs().max())
+            plan = G.L.tile_plan(a.nsig, a.nscales)
+            row = {"cfg": cfg, "ms": round(ms, 3), "frac": round(b_call / ms / 1e6 / peak, 4),
+                   "maxdiff_vs_first": err, "plan": plan.as_dict() if plan else None}
+        except Exception as exc:  # keep sweeping
+            row = {"cfg": cfg, "error": str(exc)[:200]}
+        results.append(row)
+        print(json.dumps(row), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "a") as fh:
+        for r in results:
+            fh.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()
