@@ -102,7 +102,7 @@ struct TileLayout {
   int bar_bytes;
   __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages) {
     vec_bytes = first ? 0 : (1 + nscales) * R * nsig * 4;
-    slab_bytes = (cap + 8) * 4;                 // +8: unrolled reads may run past the end
+    slab_bytes = (cap + 16) * 4;                // +16: aligned groups may run past the end
     ptr_bytes = (R + 4) * 4;
     stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;
     bar_bytes = ((2 * stages * 8 + 15) / 16) * 16;
@@ -111,7 +111,7 @@ struct TileLayout {
 };
 
 template <int G, int U, bool FIRST>
-__global__ void __launch_bounds__(32 * 17)
+__global__ void __launch_bounds__(32 * 17, U == 1 ? 2 : 1)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.rows_per_tile;
@@ -183,9 +183,16 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
 
   // ---------------------------------------------------------------- consumers
   constexpr int RP = 32 / G;               // rows in flight per warp
+  constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
   const int cw = warp - 1;
   const int sub = lane / G;
   const int c0 = (lane % G) * 4;
+  const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
+  float* __restrict__ xout = a.x_new + c0;
+  float* __restrict__ rout = a.r + c0;
+  const int64_t r_stride = a.r_rows * NS;
+  const int nscales = a.nscales;
+  const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
     const int s = it % S;
@@ -203,54 +210,79 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const int64_t row = r0 + lr;
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
-      const float4 xc = ldg_f4(a.x_cur + row * nsig + c0);
+      const unsigned span = unsigned(je - jb);
+      const float4 xc = ldg_f4(xg + row * NS);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j = jb; j < je; j += U) {
-        float4 xv[U];
-        float wv[U];
+      // The slab offset a0 is a multiple of 4, so groups of four CSR entries are
+      // 16-byte aligned in shared memory: one LDS.128 brings four column indices,
+      // one four weights.  Slots outside [jb, je) (row head / tail) are predicated
+      // off, so the sum runs over the row's entries in stored order.
+      for (int jj = jb & ~3; jj < je; jj += 4 * U) {
+        int4 c4[U];
+        float4 w4[U];
+        float4 xv[4 * U];
+        bool ok[4 * U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const bool ok = j + u < je;
-          const int col = sm_col[j + u];
-          wv[u] = ok ? sm_val[j + u] : 0.f;
-          xv[u] = ok ? ldg_f4(a.x_cur + int64_t(col) * nsig + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          c4[u] = *reinterpret_cast<const int4*>(sm_col + jj + 4 * u);
+          w4[u] = *reinterpret_cast<const float4*>(sm_val + jj + 4 * u);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          acc.x = fmaf(wv[u], xv[u].x, acc.x);
-          acc.y = fmaf(wv[u], xv[u].y, acc.y);
-          acc.z = fmaf(wv[u], xv[u].z, acc.z);
-          acc.w = fmaf(wv[u], xv[u].w, acc.w);
+          const int base = jj + 4 * u - jb;
+          ok[4 * u + 0] = unsigned(base + 0) < span;
+          ok[4 * u + 1] = unsigned(base + 1) < span;
+          ok[4 * u + 2] = unsigned(base + 2) < span;
+          ok[4 * u + 3] = unsigned(base + 3) < span;
+          if (ok[4 * u + 0]) xv[4 * u + 0] = ldg_f4(xg + int64_t(c4[u].x) * NS);
+          if (ok[4 * u + 1]) xv[4 * u + 1] = ldg_f4(xg + int64_t(c4[u].y) * NS);
+          if (ok[4 * u + 2]) xv[4 * u + 2] = ldg_f4(xg + int64_t(c4[u].z) * NS);
+          if (ok[4 * u + 3]) xv[4 * u + 3] = ldg_f4(xg + int64_t(c4[u].w) * NS);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float wq[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (ok[4 * u + q]) {
+              acc.x = fmaf(wq[q], xv[4 * u + q].x, acc.x);
+              acc.y = fmaf(wq[q], xv[4 * u + q].y, acc.y);
+              acc.z = fmaf(wq[q], xv[4 * u + q].z, acc.z);
+              acc.w = fmaf(wq[q], xv[4 * u + q].w, acc.w);
+            }
+          }
         }
       }
       float4 xn;
-      xn.x = fmaf(a.alpha, acc.x, a.beta * xc.x);
-      xn.y = fmaf(a.alpha, acc.y, a.beta * xc.y);
-      xn.z = fmaf(a.alpha, acc.z, a.beta * xc.z);
-      xn.w = fmaf(a.alpha, acc.w, a.beta * xc.w);
+      xn.x = fmaf(alpha, acc.x, beta * xc.x);
+      xn.y = fmaf(alpha, acc.y, beta * xc.y);
+      xn.z = fmaf(alpha, acc.z, beta * xc.z);
+      xn.w = fmaf(alpha, acc.w, beta * xc.w);
       if (!FIRST) {
-        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + lr * nsig + c0);
-        xn.x = fmaf(a.gamma, xo.x, xn.x);
-        xn.y = fmaf(a.gamma, xo.y, xn.y);
-        xn.z = fmaf(a.gamma, xo.z, xn.z);
-        xn.w = fmaf(a.gamma, xo.w, xn.w);
+        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + lr * NS + c0);
+        xn.x = fmaf(gamma, xo.x, xn.x);
+        xn.y = fmaf(gamma, xo.y, xn.y);
+        xn.z = fmaf(gamma, xo.z, xn.z);
+        xn.w = fmaf(gamma, xo.w, xn.w);
       }
-      stcs_f4(a.x_new + row * nsig + c0, xn);
-      for (int i = 0; i < a.nscales; ++i) {
+      stcs_f4(xout + row * NS, xn);
+      for (int i = 0; i < nscales; ++i) {
         float4 rv;
+        const float ck = a.ck[i];
         if (FIRST) {
-          rv.x = fmaf(a.ck[i], xn.x, a.half_c0[i] * xc.x);
-          rv.y = fmaf(a.ck[i], xn.y, a.half_c0[i] * xc.y);
-          rv.z = fmaf(a.ck[i], xn.z, a.half_c0[i] * xc.z);
-          rv.w = fmaf(a.ck[i], xn.w, a.half_c0[i] * xc.w);
+          const float h0 = a.half_c0[i];
+          rv.x = fmaf(ck, xn.x, h0 * xc.x);
+          rv.y = fmaf(ck, xn.y, h0 * xc.y);
+          rv.z = fmaf(ck, xn.z, h0 * xc.z);
+          rv.w = fmaf(ck, xn.w, h0 * xc.w);
         } else {
-          rv = *reinterpret_cast<const float4*>(sm_vec + (size_t(i + 1) * R + lr) * nsig + c0);
-          rv.x = fmaf(a.ck[i], xn.x, rv.x);
-          rv.y = fmaf(a.ck[i], xn.y, rv.y);
-          rv.z = fmaf(a.ck[i], xn.z, rv.z);
-          rv.w = fmaf(a.ck[i], xn.w, rv.w);
+          rv = *reinterpret_cast<const float4*>(sm_vec + (size_t(i + 1) * R + lr) * NS + c0);
+          rv.x = fmaf(ck, xn.x, rv.x);
+          rv.y = fmaf(ck, xn.y, rv.y);
+          rv.z = fmaf(ck, xn.z, rv.z);
+          rv.w = fmaf(ck, xn.w, rv.w);
         }
-        stcs_f4(a.r + (int64_t(i) * a.r_rows + row) * nsig + c0, rv);
+        stcs_f4(rout + int64_t(i) * r_stride + row * NS, rv);
       }
     }
     __syncwarp();
@@ -300,7 +332,7 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   GSP_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, st));
   GSP_CUDA(cudaStreamSynchronize(st));
   cudaFreeAsync(dmax, st);
-  const int cap = ((hmax + 8 + 63) / 64) * 64;
+  const int cap = ((hmax + 8 + 31) / 32) * 32;
   int stages = env_int("GSPB200_TILE_S", 3);
   const int warps = std::min(16, std::max(1, env_int("GSPB200_TILE_NW", 16)));
   // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
@@ -336,12 +368,9 @@ static int launch_tiled_gu(bool first, const TileArgs& a, int blocks_per_sm, cud
 
 template <int G>
 static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cudaStream_t st) {
-  switch (unroll) {
-    case 1: return launch_tiled_gu<G, 1>(first, a, bps, st);
-    case 2: return launch_tiled_gu<G, 2>(first, a, bps, st);
-    case 8: return launch_tiled_gu<G, 8>(first, a, bps, st);
-    default: return launch_tiled_gu<G, 4>(first, a, bps, st);
-  }
+  // `unroll` = neighbour packets requested back to back: 4 or 8 (groups of four entries)
+  if (unroll >= 8) return launch_tiled_gu<G, 2>(first, a, bps, st);
+  return launch_tiled_gu<G, 1>(first, a, bps, st);
 }
 
 // Rows [0, plan.rows_per_tile * n_tiles) of one step; returns the number of rows done.
