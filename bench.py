@@ -210,7 +210,33 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------- our arm
+def build_single(gsp, wl, rank):
+    """N = 1: Graph API end to end (device Laplacian, device Lanczos lmax)."""
+    W = host_graph(wl["N"], wl["k"], wl["seed"])
+    G = gsp.graphs.Graph(W)
+    G.estimate_lmax()
+    return G
+
+
+def build_partitioned(gsp, wl, rank, world, torch, dist):
+    """N > 1 (weak scaling): strip q = rank q's 1e6-vertex row block of ONE k-NN graph on
+    [0, P) x [0, 1); halo exchange per recurrence step."""
+    from pygsp_b200 import distributed as gd
+    from pygsp_b200.graphs.generators import SensorStrips, laplacian_rows
+    gen = SensorStrips(rank, world, wl["N"], k=wl["k"], seed=wl["seed"])
+    tot = torch.tensor(gen.distance_sum(), dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    sigma = float(tot[0] / tot[1])
+    L_rows, dw = laplacian_rows(gen.adjacency_rows(sigma), rank * wl["N"])
+    bound = torch.tensor([2.0 * dw.max()], dtype=torch.float64, device="cuda")
+    dist.all_reduce(bound, op=dist.ReduceOp.MAX)          # Gershgorin bound (graph.py:943-945)
+    plan = gd.HaloPlan(L_rows, gd.even_bounds(world * wl["N"], world), rank)
+    op = gd.PartitionedCheby(plan, dtype=torch.float32, overlap=True)
+    return op, float(bound.item()), int(L_rows.nnz)
+
+
 def run_ours(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     import pygsp_b200 as gsp
@@ -227,18 +253,36 @@ def run_ours(args):
     if args.n:
         wl["N"] = args.n
     n, nsig, order = wl["N"], wl["nsig"], wl["order"]
+    lib = gsp._native.lib()
+    lib.gsp_launch_count.restype = ctypes.c_uint64
 
-    # ---- build the workload (untimed): graph -> device Laplacian -> device lmax
-    W = host_graph(n, wl["k"], wl["seed"] + rank)      # weak scaling: one graph per rank
-    G = gsp.graphs.Graph(W)
-    G.estimate_lmax()
-    heat = gsp.filters.Heat(G, scale=wl["scale"])
-    c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
-    L = G.L
+    # ---- build the workload (untimed)
+    if world == 1:
+        G = build_single(gsp, wl, rank)
+        L, lmax, nnz = G.L, G.lmax, G.L.nnz
+        heat = gsp.filters.Heat(G, scale=wl["scale"])
+        c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
+        run_dev = lambda xx: apx.cheby_op_device(L, lmax, c, xx)
+        run_host = lambda xh: heat.filter(xh, order=order)
+        halo = None
+    else:
+        op, lmax, nnz = build_partitioned(gsp, wl, rank, world, torch, dist)
+
+        class _G:           # coefficients need only lmax (approximations.py:40)
+            pass
+        g = _G(); g.lmax = lmax; g.N = n
+        heat = gsp.filters.Heat(g, scale=wl["scale"])
+        c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
+        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=True)
+
+        def run_host(xh):
+            y = op.cheby_op(lmax, c, xh.to("cuda", non_blocking=True))[0]
+            out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+            out.copy_(y)
+            return out
+        halo = {"rows_received_per_rank": op.plan.n_halo, "boundary_rows": op.plan.n_true_boundary}
     gen = torch.Generator(device="cuda").manual_seed(rank)
     x = torch.randn(n, nsig, device="cuda", generator=gen)
-    lib = gsp._native.lib()
-    lib.gsp_launch_count.restype = __import__("ctypes").c_uint64
 
     def barrier():
         if world > 1:
@@ -246,8 +290,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    for _ in range(max(args.warmup, 3)):
-        apx.cheby_op_device(L, G.lmax, c, x)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        run_dev(x)
     barrier()
     launches0 = lib.gsp_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,12 +300,11 @@ def run_ours(args):
         barrier()
         start.record()
         for _ in range(args.steps):
-            apx.cheby_op_device(L, G.lmax, c, x)
+            run_dev(x)
         stop.record()
         barrier()
     launches = int(lib.gsp_launch_count() - launches0)
-    t_dev = start.elapsed_time(stop) / 1e3
-    t_all = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+    t_all = torch.tensor([start.elapsed_time(stop) / 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t_dev = float(t_all.item())
@@ -270,50 +314,53 @@ def run_ours(args):
     xh = torch.empty((n, nsig), dtype=torch.float32).pin_memory()
     xh.copy_(x)
     for _ in range(2):
-        yh = heat.filter(xh, order=order)
+        yh = run_host(xh)
     barrier()
     t0 = time.perf_counter()
-    start.record()
     for _ in range(args.steps):
-        yh = heat.filter(xh, order=order)
-    stop.record()
-    barrier()
-    t_e2e = max(start.elapsed_time(stop) / 1e3, 0.0)
-    t_wall = time.perf_counter() - t0
-    t_e2e = max(t_e2e, t_wall)       # D2H into pinned memory ends on the host side
-    t_all = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        yh = run_host(xh)
+    torch.cuda.synchronize()
+    t_all = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t_e2e = float(t_all.item())
     e2e_value = world * n * nsig * order * args.steps / t_e2e
     assert tuple(yh.shape) == (n, nsig) and not yh.is_cuda
 
+    nnz_all = torch.tensor([nnz], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(nnz_all)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (cheby_step_rowgroup, k >= 2)
-    b_first, b_step, b_call = algorithmic_bytes(n, L.nnz, nsig, 1, order)
+    # ---- roofline of the dominant kernel (one fused step, k >= 2), per GPU
+    b_first, b_step, b_call = algorithmic_bytes(n, nnz, nsig, 1, order)
     peak, peak_src = measured_peak()
-    achieved = b_call * args.steps / (t_dev if world == 1 else t_dev) / 1e9
-    t_launch = t_dev / args.steps * (b_step / b_call)
+    achieved = b_call * args.steps / t_dev / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": "cheby_step_rowgroup<float,4,16>", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_step, "avg_launch_ms": 1e3 * t_launch,
-                "timing": "CUDA events on the launching stream over the timed region"}
+                "frac": achieved / peak, "traffic": ncu_traffic(), "per_gpu": True,
+                "kernel": "cheby_step_tiled<16,1,false> (TMA-tiled fused step)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": b_step,
+                "avg_launch_ms": 1e3 * t_dev / args.steps * (b_step / b_call),
+                "timing": "CUDA events on the launching stream over the timed region, max over ranks"}
+    if halo is not None:
+        halo_bytes = halo["rows_received_per_rank"] * nsig * 4
+        halo.update({"bytes_received_per_rank_per_step": halo_bytes,
+                     "nvlink_GBps_per_rank_if_serialised": halo_bytes * order * args.steps / t_dev / 1e9,
+                     "exchange": "NCCL all_to_all_single per step, overlapped with interior rows"})
 
     # ---- CPU baseline (oracle port of the scipy path) on a bounded sample
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import pygsp_oracle as orc
         cols = args.cpu_columns
         Lh = L.to_scipy().astype(np.float64)
         xs = x[:, :cols].double().cpu().numpy()
-        t_cpu = cpu_reference_time(Lh, G.lmax, c, xs, 1)
-        ref = orc.cheby_op(Lh, G.lmax, c, xs[:, :1])
-        got = apx.cheby_op_device(L, G.lmax, c, x[:, :1].contiguous())[0].cpu().numpy()
+        t_cpu = cpu_reference_time(Lh, lmax, c, xs, 1)
+        ref = orc.cheby_op(Lh, lmax, c, xs[:, :1])
+        got = apx.cheby_op_device(L, lmax, c, x[:, :1].contiguous())[0].cpu().numpy()
         parity = float(np.abs(got - ref).max() / np.abs(ref).max())
         cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                "host_cores_available": os.cpu_count(),
@@ -322,20 +369,26 @@ def run_ours(args):
                "parity_rel_err_vs_gpu": parity}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+           "warmup": warm, "ms_per_step": 1e3 * t_dev / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": wl["name"], "N": n, "k": wl["k"], "nsig": nsig, "order": order,
-                      "nnz_L": int(L.nnz), "lmax": G.lmax, "per_gpu": "one graph per rank",
-                      "l2_policy": "inputs_exceed_l2 (working set %.2f GB per call >> 126 MB)"
-                                   % ((4 * n * nsig * 4 + 8 * L.nnz) / 1e9)},
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * nsig,
-                   "d2h_bytes_per_step": 4 * n * nsig, "ms_per_step": 1e3 * t_e2e / args.steps,
-                   "api": "pygsp_b200.filters.Heat(G, 50).filter(pinned_host_tensor, order=30)"},
-           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "config": {"workload": wl["name"], "N_per_gpu": n, "N_global": world * n, "k": wl["k"],
+                      "nsig": nsig, "order": order, "nnz_L_global": int(nnz_all.item()),
+                      "lmax": lmax,
+                      "partition": "single GPU" if world == 1 else
+                                   "1-D vertex partition, %d row blocks (strips), halo all-to-all-v "
+                                   "per step" % world,
+                      "l2_policy": "inputs_exceed_l2 (working set %.2f GB per GPU per call >> 126 MB)"
+                                   % ((4 * n * nsig * 4 + 8 * nnz) / 1e9)},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * nsig * world,
+                   "d2h_bytes_per_step": 4 * n * nsig * world, "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "api": "Heat(G, 50).filter(pinned_host_tensor, order=30)" if world == 1 else
+                          "PartitionedCheby.cheby_op(pinned host block -> H2D -> op -> D2H)"},
+           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "halo": halo,
            "clocks": clocks.summary()}
     print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

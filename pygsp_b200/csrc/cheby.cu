@@ -26,7 +26,7 @@
 
 namespace gsp {
 
-int cheby_step_tiled_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const int32_t* indptr,
                          const int32_t* indices, const float* vals, const float* x_cur,
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
@@ -252,7 +252,7 @@ static int cheby_step_planned(const gsp_tile_plan* plan, int64_t nnz, bool first
                        nscales, ck, c0, alpha, beta, gamma, st);
 }
 
-// float32 with a tile plan: TMA-tiled kernel on the full tiles of [0, re), the
+// float32 with a tile plan: TMA-tiled kernel on the full tiles of [rb, re), the
 // row-group kernel on the remaining (< rows_per_tile) rows.
 template <>
 int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first, int64_t rb,
@@ -261,13 +261,13 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
                               float* x_new, float* r, int64_t r_rows, int nsig, int nscales,
                               const double* ck, const double* c0, double alpha, double beta,
                               double gamma, cudaStream_t st) {
-  const bool tiled = plan && plan->rows_per_tile > 0 && rb == 0 && nscales <= kMaxScales &&
+  const bool tiled = plan && plan->rows_per_tile > 0 && rb % 4 == 0 && nscales <= kMaxScales &&
                      aligned16(indptr) && aligned16(indices) && aligned16(vals) &&
                      aligned16(x_cur) && aligned16(x_new) && aligned16(r) &&
                      (first || aligned16(x_old));
   int64_t done = 0;
   if (tiled) {
-    int rc = cheby_step_tiled_f32(first, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
+    int rc = cheby_step_tiled_f32(first, rb, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
                                   r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, &done,
                                   st);
     if (rc != GSP_OK) return rc;

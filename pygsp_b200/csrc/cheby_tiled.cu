@@ -28,6 +28,7 @@ constexpr int kTiledMaxScales = 16;
 
 struct TileArgs {
   int64_t n_tiles;
+  int64_t row_begin;   // first row of tile 0 (multiple of 4)
   int64_t r_rows;
   int64_t nnz;
   const int32_t* indptr;
@@ -150,7 +151,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
       int32_t* sm_meta = sm_ptr + (R + 4);
 
-      const int64_t r0 = tile * R;
+      const int64_t r0 = a.row_begin + tile * R;
       const int begin = __ldg(a.indptr + r0);
       const int end = __ldg(a.indptr + r0 + R);
       const int a0 = begin & ~3;                    // 16-byte aligned slab start
@@ -204,7 +205,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     const float* sm_val = reinterpret_cast<const float*>(st + lay.vec_bytes + lay.slab_bytes);
     const int32_t* sm_ptr = reinterpret_cast<const int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
     const int a0 = sm_ptr[R + 4];
-    const int64_t r0 = tile * R;
+    const int64_t r0 = a.row_begin + tile * R;
 
     for (int lr = cw * RP + sub; lr < R; lr += NW * RP) {
       const int64_t row = r0 + lr;
@@ -290,14 +291,17 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   }
 }
 
-// max over tiles of the 16-byte-aligned CSR slab length of a tile
-__global__ void tile_nnz_max_kernel(int64_t n_tiles, int rows_per_tile,
+// max over every window of `rows_per_tile` rows that starts at a multiple of 4 of
+// the window's 16-byte-aligned CSR slab length: a bound valid for any tiling of
+// any row range [rb, re) with rb % 4 == 0
+__global__ void tile_nnz_max_kernel(int64_t n, int rows_per_tile,
                                     const int32_t* __restrict__ indptr, int* out) {
   int best = 0;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n_tiles;
-       t += int64_t(gridDim.x) * blockDim.x) {
-    const int begin = indptr[t * rows_per_tile] & ~3;
-    const int end = (indptr[(t + 1) * rows_per_tile] + 3) & ~3;
+  const int64_t windows = (n - rows_per_tile) / 4 + 1;
+  for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < windows;
+       w += int64_t(gridDim.x) * blockDim.x) {
+    const int begin = indptr[4 * w] & ~3;
+    const int end = (indptr[4 * w + rows_per_tile] + 3) & ~3;
     best = max(best, end - begin);
   }
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -325,8 +329,8 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   int* dmax = nullptr;
   GSP_CUDA(cudaMallocAsync((void**)&dmax, sizeof(int), st));
   GSP_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), st));
-  const int blocks = (int)std::min<int64_t>(ceil_div(n_tiles, 256), 1024);
-  tile_nnz_max_kernel<<<blocks, 256, 0, st>>>(n_tiles, R, indptr, dmax);
+  const int blocks = (int)std::min<int64_t>(ceil_div(n / 4 + 1, 256), 2048);
+  tile_nnz_max_kernel<<<blocks, 256, 0, st>>>(n, R, indptr, dmax);
   GSP_LAUNCH_CHECK("tile_nnz_max");
   int hmax = 0;
   GSP_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -373,15 +377,16 @@ static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cu
   return launch_tiled_gu<G, 1>(first, a, bps, st);
 }
 
-// Rows [0, plan.rows_per_tile * n_tiles) of one step; returns the number of rows done.
-int cheby_step_tiled_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+// Full tiles of rows [rb, re) of one step (rb % 4 == 0); reports the number of rows done.
+int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const int32_t* indptr,
                          const int32_t* indices, const float* vals, const float* x_cur,
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, int64_t* rows_done,
                          cudaStream_t st) {
   TileArgs a;
-  a.n_tiles = n / plan.rows_per_tile;
+  a.row_begin = rb;
+  a.n_tiles = (re - rb) / plan.rows_per_tile;
   *rows_done = a.n_tiles * plan.rows_per_tile;
   if (a.n_tiles == 0) return GSP_OK;
   a.r_rows = r_rows;

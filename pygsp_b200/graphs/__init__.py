@@ -1,4 +1,5 @@
 """Graph object and the generators the BASELINE configurations use."""
 from .csr import DeviceCSR  # noqa: F401
 from .graph import Graph  # noqa: F401
-from .generators import Grid2d, Logo, NNGraph, Ring, Sensor, morton_order  # noqa: F401
+from .generators import (Grid2d, Logo, NNGraph, Ring, Sensor, SensorStrips,  # noqa: F401
+                         laplacian_rows, morton_order)

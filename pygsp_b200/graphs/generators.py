@@ -145,3 +145,76 @@ class Sensor(NNGraph):
         coords = np.random.default_rng(seed).uniform(0, 1, (N, 2))
         kwargs.setdefault("plotting", {"limits": np.array([0, 1, 0, 1])})
         super().__init__(coords, k=k, center=False, rescale=False, order=order, **kwargs)
+
+
+class SensorStrips:
+    r"""Row block of a Sensor-type k-NN graph on the strip domain [0, P) x [0, 1).
+
+    Weak-scaling input of the partitioned path: strip q holds ``n_per`` uniform
+    points (``default_rng(seed + q)``, Morton-numbered inside the strip, global ids
+    q*n_per ...), every strip is one rank's row block.  A rank regenerates its two
+    neighbour strips, so no point data crosses ranks; the graph is exactly the k-NN
+    graph of the union of all strips with NNGraph's weights and 'average'
+    symmetrisation (nngraph.py:218-226,289-297), as ``tests`` check against a
+    directly built global graph.  Host-side input fabrication (scipy cKDTree).
+    """
+
+    def __init__(self, rank, parts, n_per, k=10, seed=0):
+        self.rank, self.parts, self.n_per, self.k = rank, parts, n_per, k
+        self.strips = [q for q in (rank - 1, rank, rank + 1) if 0 <= q < parts]
+        pts = []
+        for q in self.strips:
+            p = np.random.default_rng(seed + q).uniform(0, 1, (n_per, 2))
+            p = p[morton_order(p)]
+            p[:, 0] += q
+            pts.append(p)
+        self.points = np.concatenate(pts)
+        self.own_lo = self.strips.index(rank) * n_per
+        own = np.arange(self.own_lo, self.own_lo + n_per)
+        margin = 8.0 * np.sqrt(k / (np.pi * n_per))
+        x = self.points[:, 0]
+        near = (np.abs(x - rank) < margin) | (np.abs(x - (rank + 1)) < margin)
+        near[own] = False
+        self.sel = np.concatenate([own, np.flatnonzero(near)])
+        tree = spatial.cKDTree(self.points)
+        self.D, self.NN = tree.query(self.points[self.sel], k=k + 1, workers=-1)
+        if self.D[:, -1].max() * 2 >= margin:
+            raise RuntimeError("strip margin too small for this density")
+        self.coords = self.points[own]
+
+    def distance_sum(self):
+        """(sum, count) of the own points' neighbour distances: sigma = global mean."""
+        d = self.D[:self.n_per, 1:]
+        return float(d.sum()), int(d.size)
+
+    def adjacency_rows(self, sigma):
+        """W[rows of this rank, :] as CSR with GLOBAL column ids."""
+        m, k = self.points.shape[0], self.k
+        src = np.repeat(self.sel, k)
+        A = sparse.csr_matrix((np.exp(-self.D[:, 1:].ravel() ** 2 / float(sigma)),
+                               (src, self.NN[:, 1:].ravel())), shape=(m, m))
+        S = ((A + A.T) / 2).tocsr()[self.own_lo:self.own_lo + self.n_per]
+        S.sort_indices()
+        local = S.indices.astype(np.int64)
+        strip = np.asarray(self.strips, dtype=np.int64)[local // self.n_per]
+        gcol = strip * self.n_per + local % self.n_per
+        n_global = self.parts * self.n_per
+        # global ids keep the local order inside a strip and strips are ascending,
+        # so the columns stay sorted
+        return sparse.csr_matrix((S.data, gcol, S.indptr), shape=(self.n_per, n_global))
+
+
+def laplacian_rows(W_rows, row_offset):
+    """Rows of the combinatorial Laplacian D - W from rows of a SYMMETRIC adjacency.
+
+    Host helper of the partitioned path: dw of a row block is its row sums, so the
+    rows of L are built without the rest of the matrix (graph.py:618-620)."""
+    W_rows = W_rows.tocsr()
+    n_local, n = W_rows.shape
+    dw = np.asarray(W_rows.sum(axis=1)).ravel()
+    D = sparse.csr_matrix((dw, (np.arange(n_local), np.arange(n_local) + row_offset)),
+                          shape=(n_local, n))
+    L = (D - W_rows).tocsr()
+    L.eliminate_zeros()
+    L.sort_indices()
+    return L, dw
