@@ -104,10 +104,10 @@ def main():
 
     if backend == "nccl":
         # bit-identical to the single-GPU engine on the full graph (same accumulation order)
-        import pygsp_b200 as gsp
         from pygsp_b200.filters import approximations as apx
-        G = gsp.graphs.Graph(W)
-        full = apx.cheby_op_device(G.L, lmax, c, torch.from_numpy(x).to(op.device, dtype))
+        from pygsp_b200.graphs import DeviceCSR
+        Ld = DeviceCSR.from_scipy(L, dtype, op.device)        # the same float32 values of L
+        full = apx.cheby_op_device(Ld, lmax, c, torch.from_numpy(x).to(op.device, dtype))
         mine = op.cheby_op(lmax, c, xl)
         assert torch.equal(mine, full[:, lo:hi]), float((mine - full[:, lo:hi]).abs().max())
     dist.barrier()

@@ -35,7 +35,7 @@ def run_world(backend, world, n, nsig, nscales, order, overlap=0, timeout=300):
             if p.poll() is None:
                 p.kill()
     for r, (p, o) in enumerate(zip(procs, outs)):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-3000:])
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-1500:])
         assert "rank %d ok" % r in o
     return outs
 
