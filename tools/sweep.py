@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--nscales", type=int, default=1)
     ap.add_argument("--order", type=int, default=30)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--graph", default="sensor", choices=["sensor", "grid2d"])
+    ap.add_argument("--bank", default="heat", choices=["heat", "mexicanhat"])
     ap.add_argument("configs", nargs="*")
     a = ap.parse_args()
     import torch
@@ -32,11 +34,20 @@ def main():
     import pygsp_b200 as gsp
     from pygsp_b200.filters import approximations as apx
 
-    W = bench.host_graph(a.n, 10, 0)
-    G = gsp.graphs.Graph(W)
+    if a.graph == "grid2d":
+        side = int(round(a.n ** 0.5))
+        G = gsp.graphs.Grid2d(side, side)
+        a.n = G.N
+    else:
+        G = gsp.graphs.Graph(bench.host_graph(a.n, 10, 0))
     G.estimate_lmax()
-    taus = [50.0 / (i + 1) for i in range(a.nscales)]
-    c = np.atleast_2d(np.array(gsp.filters.compute_cheby_coeff(gsp.filters.Heat(G, taus), m=a.order)))
+    if a.bank == "mexicanhat":
+        filt = gsp.filters.MexicanHat(G, Nf=a.nscales)
+    else:
+        filt = gsp.filters.Heat(G, [50.0 / (i + 1) for i in range(a.nscales)])
+    c = np.atleast_2d(np.array(gsp.filters.compute_cheby_coeff(filt, m=a.order)))
+    print(json.dumps({"graph": a.graph, "N": G.N, "nnz_L": G.L.nnz, "lmax": G.lmax,
+                      "lanczos_steps": G._lanczos_steps}), flush=True)
     x = torch.randn(a.n, a.nsig, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
     _, _, b_call = bench.algorithmic_bytes(a.n, G.L.nnz, a.nsig, a.nscales, a.order)
     peak, _ = bench.measured_peak()
@@ -65,6 +76,7 @@ def main():
             err = float((y - ref).abs().max() / ref.abs().max())
             plan = G.L.tile_plan(a.nsig, a.nscales)
             row = {"cfg": cfg, "ms": round(ms, 3), "frac": round(b_call / ms / 1e6 / peak, 4),
+                   "units_per_s": a.n * a.nsig * a.order / ms * 1e3,
                    "maxdiff_vs_first": err, "plan": plan.as_dict() if plan else None}
         except Exception as exc:  # keep sweeping
             row = {"cfg": cfg, "error": str(exc)[:200]}
