@@ -145,32 +145,49 @@ def ncu_traffic():
 
 
 # -------------------------------------------------------------- CPU reference
-def _cpu_worker(args):
-    Lparts, lmax, c, x = args
-    from scipy import sparse
+_REF = {}          # inherited by the forked workers: nothing big is pickled per task
+
+
+def _cpu_worker(cols):
     from oracle import pygsp_oracle as orc
-    L = sparse.csr_matrix(Lparts[:3], shape=Lparts[3])
-    t0 = time.perf_counter()
-    orc.cheby_op(L, lmax, c, x)
-    return time.perf_counter() - t0
+    lo, hi = cols
+    orc.cheby_op(_REF["L"], _REF["lmax"], _REF["c"], _REF["x"][:, lo:hi])
+    return hi - lo
+
+
+class CpuReference:
+    """The oracle port (scipy csr_matvecs + numpy, float64 -- the reference's own
+    arithmetic, approximations.py:58-114) with the signal columns sharded over
+    `procs` forked processes (the reference itself is single-threaded)."""
+
+    def __init__(self, L, lmax, c, x, procs):
+        import multiprocessing as mp
+        _REF.update(L=L, lmax=lmax, c=c, x=np.ascontiguousarray(x))
+        self.procs = max(1, min(procs, x.shape[1]))
+        edges = np.linspace(0, x.shape[1], self.procs + 1).astype(int)
+        self.chunks = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        self.pool = mp.get_context("fork").Pool(self.procs) if self.procs > 1 else None
+
+    def time_once(self):
+        t0 = time.perf_counter()
+        if self.pool is None:
+            _cpu_worker(self.chunks[0])
+        else:
+            self.pool.map(_cpu_worker, self.chunks, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
 
 
 def cpu_reference_time(L, lmax, c, x, procs):
-    """Wall time of the oracle port (scipy csr_matvecs + numpy, float64 -- the
-    reference's arithmetic) on `x`, signal columns sharded over `procs` processes."""
-    from oracle import pygsp_oracle as orc
-    if procs <= 1:
-        t0 = time.perf_counter()
-        orc.cheby_op(L, lmax, c, x)
-        return time.perf_counter() - t0
-    import multiprocessing as mp
-    parts = (L.data, L.indices, L.indptr, L.shape)
-    chunks = [np.ascontiguousarray(a) for a in np.array_split(x, procs, axis=1) if a.shape[1]]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(len(chunks)) as pool:
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(parts, lmax, c, ch) for ch in chunks])
-        return time.perf_counter() - t0
+    ref = CpuReference(L, lmax, c, x, procs)
+    try:
+        return ref.time_once()
+    finally:
+        ref.close()
 
 
 def run_reference(args):
@@ -188,11 +205,13 @@ def run_reference(args):
     L = orc.laplacian(W)
     lmax = orc.upper_bound(W)                  # estimate_lmax(method="bounds"): deterministic
     c = orc.cheby_coeff(orc.heat_kernels(lmax, wl["scale"]), lmax, wl["order"])
-    ncols = procs                               # bounded sample: one signal column per process
+    ncols = min(wl["nsig"], procs)              # bounded sample: one signal column per process
     x = np.random.default_rng(0).standard_normal((wl["N"], ncols))
+    ref = CpuReference(L, lmax, c, x, procs)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_time(L, lmax, c, x, procs)
-    times = [cpu_reference_time(L, lmax, c, x, procs) for _ in range(args.steps)]
+        ref.time_once()
+    times = [ref.time_once() for _ in range(args.steps)]
+    ref.close()
     t = float(np.sum(times))
     value = wl["N"] * ncols * wl["order"] * args.steps / t
     sample = "%d of %d signal columns per step (one per process), full graph, full order" % (

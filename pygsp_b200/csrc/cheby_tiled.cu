@@ -105,14 +105,14 @@ struct TileLayout {
     vec_bytes = first ? 0 : (1 + nscales) * R * nsig * 4;
     slab_bytes = (cap + 16) * 4;                // +16: aligned groups may run past the end
     ptr_bytes = (R + 4) * 4;
-    stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;
+    stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;   // +16: slab offset, group counter
     bar_bytes = ((2 * stages * 8 + 15) / 16) * 16;
   }
   __host__ __device__ int total(int stages) const { return bar_bytes + stages * stage_bytes; }
 };
 
-template <int G, int U, bool FIRST>
-__global__ void __launch_bounds__(32 * 17, U == 1 ? 2 : 1)
+template <int G, int U, bool FIRST, int NSC, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 32 * 17, (BIG || U != 1) ? 1 : 2)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.rows_per_tile;
@@ -130,7 +130,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, NW);
+      mbar_init(empty + s, uint32_t(R / (32 / G)));
+      // row-group ticket counter of the stage: monotonic over rounds, never reset
+      unsigned char* st0 = stage0 + size_t(s) * lay.stage_bytes;
+      reinterpret_cast<int32_t*>(st0 + lay.vec_bytes + 2 * lay.slab_bytes)[R + 5] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,36 +186,57 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   }
 
   // ---------------------------------------------------------------- consumers
-  constexpr int RP = 32 / G;               // rows in flight per warp
+  // Row groups (32/G rows, one per lane group) are handed out dynamically from a
+  // counter in the stage: a warp that draws short rows simply draws again, so no
+  // warp waits on a slower one inside a tile, and a stage is released when all of
+  // its row groups have been completed (the empty barrier counts row groups).
+  constexpr int RP = 32 / G;               // rows per row group
   constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
-  const int cw = warp - 1;
   const int sub = lane / G;
   const int c0 = (lane % G) * 4;
   const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
-  float* __restrict__ xout = a.x_new + c0;
-  float* __restrict__ rout = a.r + c0;
-  const int64_t r_stride = a.r_rows * NS;
-  const int nscales = a.nscales;
+  const int groups = R / RP;
+  const int nscales = NSC >= 0 ? NSC : a.nscales;
   const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
     const int s = it % S;
     const uint32_t round = uint32_t(it / S);
     mbar_wait(full + s, round & 1u);
-    const unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
+    unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
     const float* sm_vec = reinterpret_cast<const float*>(st);
     const int32_t* sm_col = reinterpret_cast<const int32_t*>(st + lay.vec_bytes);
     const float* sm_val = reinterpret_cast<const float*>(st + lay.vec_bytes + lay.slab_bytes);
-    const int32_t* sm_ptr = reinterpret_cast<const int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
+    int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
     const int a0 = sm_ptr[R + 4];
     const int64_t r0 = a.row_begin + tile * R;
+    const float* __restrict__ xc_tile = xg + r0 * NS;
+    float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
+    float* __restrict__ r_tile = a.r + r0 * NS + c0;
+    const int64_t r_stride = a.r_rows * NS;
 
-    for (int lr = cw * RP + sub; lr < R; lr += NW * RP) {
-      const int64_t row = r0 + lr;
+    const int ticket_base = int(round) * groups;
+    for (;;) {
+      // take the next ticket of this round, if any is left (a failed attempt must
+      // not advance the counter: a late warp of round r has to fail in round r+1 too)
+      int grp = -1;
+      if (lane == 0) {
+        int* ctr = sm_ptr + R + 5;
+        int cur = *reinterpret_cast<volatile int*>(ctr);
+        while (cur < ticket_base + groups) {
+          const int seen = atomicCAS(ctr, cur, cur + 1);
+          if (seen == cur) { grp = cur - ticket_base; break; }
+          cur = seen;
+        }
+      }
+      grp = __shfl_sync(0xffffffffu, grp, 0);
+      if (grp < 0) break;
+      const int lr = grp * RP + sub;
+      const int off = lr * NS;
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
       const unsigned span = unsigned(je - jb);
-      const float4 xc = ldg_f4(xg + row * NS);
+      const float4 xc = ldg_f4(xc_tile + off);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       // The slab offset a0 is a multiple of 4, so groups of four CSR entries are
       // 16-byte aligned in shared memory: one LDS.128 brings four column indices,
@@ -260,14 +284,16 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       xn.z = fmaf(alpha, acc.z, beta * xc.z);
       xn.w = fmaf(alpha, acc.w, beta * xc.w);
       if (!FIRST) {
-        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + lr * NS + c0);
+        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + off + c0);
         xn.x = fmaf(gamma, xo.x, xn.x);
         xn.y = fmaf(gamma, xo.y, xn.y);
         xn.z = fmaf(gamma, xo.z, xn.z);
         xn.w = fmaf(gamma, xo.w, xn.w);
       }
-      stcs_f4(xout + row * NS, xn);
-      for (int i = 0; i < nscales; ++i) {
+      stcs_f4(xn_tile + off, xn);
+#pragma unroll
+      for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
+        if (NSC < 0 && i >= nscales) break;
         float4 rv;
         const float ck = a.ck[i];
         if (FIRST) {
@@ -277,17 +303,17 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           rv.z = fmaf(ck, xn.z, h0 * xc.z);
           rv.w = fmaf(ck, xn.w, h0 * xc.w);
         } else {
-          rv = *reinterpret_cast<const float4*>(sm_vec + (size_t(i + 1) * R + lr) * NS + c0);
+          rv = *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
           rv.x = fmaf(ck, xn.x, rv.x);
           rv.y = fmaf(ck, xn.y, rv.y);
           rv.z = fmaf(ck, xn.z, rv.z);
           rv.w = fmaf(ck, xn.w, rv.w);
         }
-        stcs_f4(rout + int64_t(i) * r_stride + row * NS, rv);
+        stcs_f4(r_tile + i * r_stride + off, rv);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);        // one row group of this stage is done
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + s);
   }
 }
 
@@ -338,7 +364,7 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   cudaFreeAsync(dmax, st);
   const int cap = ((hmax + 8 + 31) / 32) * 32;
   int stages = env_int("GSPB200_TILE_S", 3);
-  const int warps = std::min(16, std::max(1, env_int("GSPB200_TILE_NW", 16)));
+  const int warps = std::min(31, std::max(1, env_int("GSPB200_TILE_NW", 16)));
   // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
   const int budget = env_int("GSPB200_TILE_SMEM", 100 * 1024);
   TileLayout lay(R, cap, (int)nsig, nscales, false, stages);
@@ -353,12 +379,12 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   return GSP_OK;
 }
 
-template <int G, int U>
-static int launch_tiled_gu(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
+template <int G, int U, int NSC, bool BIG>
+static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
   const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages);
   const int smem = lay.total(a.stages);
   const int threads = 32 * (1 + a.consumer_warps);
-  auto kern = first ? cheby_step_tiled<G, U, true> : cheby_step_tiled<G, U, false>;
+  auto kern = first ? cheby_step_tiled<G, U, true, NSC, BIG> : cheby_step_tiled<G, U, false, NSC, BIG>;
   GSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
   GSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -370,11 +396,26 @@ static int launch_tiled_gu(bool first, const TileArgs& a, int blocks_per_sm, cud
   return GSP_OK;
 }
 
+template <int G, int U, bool BIG>
+static int launch_tiled_gu(bool first, const TileArgs& a, int bps, cudaStream_t st) {
+  switch (a.nscales) {          // common bank widths get the scale loop unrolled
+    case 0: return launch_tiled_k<G, U, 0, BIG>(first, a, bps, st);
+    case 1: return launch_tiled_k<G, U, 1, BIG>(first, a, bps, st);
+    case 2: return launch_tiled_k<G, U, 2, BIG>(first, a, bps, st);
+    default: return launch_tiled_k<G, U, -1, BIG>(first, a, bps, st);
+  }
+}
+
 template <int G>
 static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cudaStream_t st) {
   // `unroll` = neighbour packets requested back to back: 4 or 8 (groups of four entries)
-  if (unroll >= 8) return launch_tiled_gu<G, 2>(first, a, bps, st);
-  return launch_tiled_gu<G, 1>(first, a, bps, st);
+  const bool big = a.consumer_warps > 16;
+  if (unroll >= 8) {
+    return big ? launch_tiled_gu<G, 2, true>(first, a, bps, st)
+               : launch_tiled_gu<G, 2, false>(first, a, bps, st);
+  }
+  return big ? launch_tiled_gu<G, 1, true>(first, a, bps, st)
+             : launch_tiled_gu<G, 1, false>(first, a, bps, st);
 }
 
 // Full tiles of rows [rb, re) of one step (rb % 4 == 0); reports the number of rows done.
