@@ -130,10 +130,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, uint32_t(R / (32 / G)));
-      // row-group ticket counter of the stage: monotonic over rounds, never reset
-      unsigned char* st0 = stage0 + size_t(s) * lay.stage_bytes;
-      reinterpret_cast<int32_t*>(st0 + lay.vec_bytes + 2 * lay.slab_bytes)[R + 5] = 0;
+      mbar_init(empty + s, NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,9 +140,23 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     // ------------------------------------------------------------- producer
     if (lane != 0) return;
     int it = 0;
+    // the tile's first / last CSR offsets are fetched one tile ahead, so that their
+    // DRAM latency is not in series with the wait for a free slot
+    int nbegin = 0, nend = 0;
+    if (int64_t(blockIdx.x) < a.n_tiles) {
+      const int64_t rn = a.row_begin + int64_t(blockIdx.x) * R;
+      nbegin = __ldg(a.indptr + rn);
+      nend = __ldg(a.indptr + rn + R);
+    }
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int s = it % S;
       const uint32_t round = uint32_t(it / S);
+      const int begin = nbegin, end = nend;
+      if (tile + gridDim.x < a.n_tiles) {
+        const int64_t rn = a.row_begin + (tile + gridDim.x) * R;
+        nbegin = __ldg(a.indptr + rn);
+        nend = __ldg(a.indptr + rn + R);
+      }
       mbar_wait(empty + s, (round & 1u) ^ 1u);      // slot free (passes at once in round 0)
       unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
       float* sm_vec = reinterpret_cast<float*>(st);
@@ -155,8 +166,6 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       int32_t* sm_meta = sm_ptr + (R + 4);
 
       const int64_t r0 = a.row_begin + tile * R;
-      const int begin = __ldg(a.indptr + r0);
-      const int end = __ldg(a.indptr + r0 + R);
       const int a0 = begin & ~3;                    // 16-byte aligned slab start
       int a1 = (end + 3) & ~3;
       if (int64_t(a1) > a.nnz) a1 = end & ~3;      // never read past the arrays
@@ -186,16 +195,12 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   }
 
   // ---------------------------------------------------------------- consumers
-  // Row groups (32/G rows, one per lane group) are handed out dynamically from a
-  // counter in the stage: a warp that draws short rows simply draws again, so no
-  // warp waits on a slower one inside a tile, and a stage is released when all of
-  // its row groups have been completed (the empty barrier counts row groups).
-  constexpr int RP = 32 / G;               // rows per row group
+  constexpr int RP = 32 / G;               // rows in flight per warp
+  const int cw = warp - 1;
   constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
   const int sub = lane / G;
   const int c0 = (lane % G) * 4;
   const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
-  const int groups = R / RP;
   const int nscales = NSC >= 0 ? NSC : a.nscales;
   const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
   int it = 0;
@@ -215,23 +220,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     float* __restrict__ r_tile = a.r + r0 * NS + c0;
     const int64_t r_stride = a.r_rows * NS;
 
-    const int ticket_base = int(round) * groups;
-    for (;;) {
-      // take the next ticket of this round, if any is left (a failed attempt must
-      // not advance the counter: a late warp of round r has to fail in round r+1 too)
-      int grp = -1;
-      if (lane == 0) {
-        int* ctr = sm_ptr + R + 5;
-        int cur = *reinterpret_cast<volatile int*>(ctr);
-        while (cur < ticket_base + groups) {
-          const int seen = atomicCAS(ctr, cur, cur + 1);
-          if (seen == cur) { grp = cur - ticket_base; break; }
-          cur = seen;
-        }
-      }
-      grp = __shfl_sync(0xffffffffu, grp, 0);
-      if (grp < 0) break;
-      const int lr = grp * RP + sub;
+    for (int lr = cw * RP + sub; lr < R; lr += NW * RP) {
       const int off = lr * NS;
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
@@ -311,9 +300,9 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
         }
         stcs_f4(r_tile + i * r_stride + off, rv);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);        // one row group of this stage is done
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
   }
 }
 
@@ -347,7 +336,8 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   if (force && strcmp(force, "rowgroup") == 0) return GSP_OK;
   if (!(nsig == 32 || nsig == 64 || nsig == 128)) return GSP_OK;
   if (nscales < 0 || nscales > kTiledMaxScales) return GSP_OK;
-  int R = env_int("GSPB200_TILE_R", nscales <= 2 ? 32 : 16);
+  // vector tiles per stage: x_old + one r tile per scale; keep a stage near 40 KB
+  int R = env_int("GSPB200_TILE_R", nscales <= 1 ? 64 : (nscales <= 2 ? 32 : 16));
   if (nsig == 128) R = std::max(8, R / 2);
   R = std::max(8, (R / 8) * 8);
   const int64_t n_tiles = n / R;
@@ -363,7 +353,7 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   GSP_CUDA(cudaStreamSynchronize(st));
   cudaFreeAsync(dmax, st);
   const int cap = ((hmax + 8 + 31) / 32) * 32;
-  int stages = env_int("GSPB200_TILE_S", 3);
+  int stages = env_int("GSPB200_TILE_S", nscales <= 1 ? 2 : 3);
   const int warps = std::min(31, std::max(1, env_int("GSPB200_TILE_NW", 16)));
   // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
   const int budget = env_int("GSPB200_TILE_SMEM", 100 * 1024);
