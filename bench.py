@@ -251,7 +251,8 @@ def build_partitioned(gsp, wl, rank, world, torch, dist):
     dist.all_reduce(bound, op=dist.ReduceOp.MAX)          # Gershgorin bound (graph.py:943-945)
     plan = gd.HaloPlan(L_rows, gd.even_bounds(world * wl["N"], world), rank)
     ov = os.environ.get("GSPB200_OVERLAP")          # default: decided from the halo size
-    op = gd.PartitionedCheby(plan, dtype=torch.float32, overlap=None if ov is None else ov != "0")
+    op = gd.PartitionedCheby(plan, dtype=torch.float32, overlap=None if ov is None else ov != "0",
+                             exchange=os.environ.get("GSPB200_EXCHANGE"))   # default: p2p
     return op, float(bound.item()), int(L_rows.nnz)
 
 
@@ -369,7 +370,7 @@ def run_ours(args):
         halo_bytes = halo["rows_received_per_rank"] * nsig * 4
         halo.update({"bytes_received_per_rank_per_step": halo_bytes,
                      "nvlink_GBps_per_rank_if_serialised": halo_bytes * order * args.steps / t_dev / 1e9,
-                     "exchange": "NCCL all_to_all_single per step (split + overlapped with interior rows when the halo exceeds 16 MB)"})
+                     "exchange": os.environ.get("GSPB200_EXCHANGE") or "p2p: peer stores over NVLink into the neighbours' halo rows + flag wait (csrc/halo.cu); NCCL all_to_all_single available with GSPB200_EXCHANGE=nccl"})
 
     # ---- CPU baseline (oracle port of the scipy path) on a bounded sample
     cpu = None

@@ -115,6 +115,31 @@ int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, co
  * gsp_gather_rows_* / gsp_scatter_rows_*  dst[i,:] = src[idx[i],:] / dst[idx[i],:] = src[i,:]
  *     (vertex reordering in and out, halo packing).
  */
+/* ------------------------------------------------------------ peer-memory halo ---
+ * The vertex-partitioned path (no reference counterpart: PyGSP is single-process).
+ * gsp_ipc_alloc / open / close / free: cudaMalloc'ed, zero-filled buffers exported with
+ *     CUDA IPC (64-byte handle) so that the other ranks of the node can map them.
+ * gsp_halo_push_*: copies rows src[src_row[e], :] into peer_base[dst_peer[e]][dst_row[e], :]
+ *     (peer stores over NVLink), fences, then writes `value` to every peer_flags[q]
+ *     (the address of this rank's slot in neighbour q's flag array).
+ *     done_counter: one zero-initialised device uint32 owned by the caller.
+ * gsp_halo_wait: blocks the STREAM (not the host) until flags[neighbor_ids[q]] >= value.
+ */
+int gsp_ipc_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle64_out);
+int gsp_ipc_open(const unsigned char* handle64, void** dev_ptr_out);
+int gsp_ipc_close(void* dev_ptr);
+int gsp_ipc_free(void* dev_ptr);
+int gsp_halo_push_f32(int64_t n_send, const int64_t* src_row, const int32_t* dst_peer,
+                      const int64_t* dst_row, const float* src, float* const* peer_base,
+                      int64_t width, uint64_t* const* peer_flags, int n_neighbors,
+                      uint64_t value, uint32_t* done_counter, void* stream);
+int gsp_halo_push_f64(int64_t n_send, const int64_t* src_row, const int32_t* dst_peer,
+                      const int64_t* dst_row, const double* src, double* const* peer_base,
+                      int64_t width, uint64_t* const* peer_flags, int n_neighbors,
+                      uint64_t value, uint32_t* done_counter, void* stream);
+int gsp_halo_wait(const uint64_t* flags, const int32_t* neighbor_ids, int n_neighbors,
+                  uint64_t value, void* stream);
+
 #define GSPB200_DECLARE_GRAPH_API(SUF, T)                                                        \
   int gsp_csr_inspect_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,            \
                             const T* data, int64_t* stats_dev, void* stream);                    \

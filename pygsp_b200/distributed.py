@@ -138,9 +138,16 @@ class PartitionedCheby:
     fallback: without an injected backend a CUDA device is required.
     """
 
-    def __init__(self, plan, dtype=None, device=None, group=None, backend=None, overlap=None):
+    def __init__(self, plan, dtype=None, device=None, group=None, backend=None, overlap=None,
+                 exchange=None):
         import torch
         self.plan, self.group = plan, group
+        # 'p2p': boundary rows are stored straight into the neighbours' halo rows over
+        # NVLink peer memory, flags order the steps (csrc/halo.cu); 'nccl': pack +
+        # all_to_all_single.  Default: p2p on GPUs, collective on the CPU test backend.
+        self.exchange = exchange
+        self._windows = {}
+        self._seq = 0
         self.backend = backend if backend is not None else _CudaBackend(device)
         self.device = self.backend.device
         self.dtype = dtype if dtype is not None else torch.float32
@@ -196,6 +203,9 @@ class PartitionedCheby:
         nsig = int(x.shape[1])
         n, nb = p.n_local, p.n_boundary
         ext = n + p.n_halo
+        mode = self.exchange or ("p2p" if self.backend.has_streams and p.parts > 1 else "nccl")
+        if mode == "p2p":
+            return self._cheby_op_p2p(lmax, c, x, local_order)
         bufs = [torch.empty((ext, nsig), dtype=self.dtype, device=self.device) for _ in range(2)]
         xin = x.to(self.dtype)
         bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
@@ -233,6 +243,178 @@ class PartitionedCheby:
         out = torch.empty_like(r)
         out[:, self.perm] = r
         return out
+
+
+def _cheby_op_p2p(self, lmax, c, x, local_order):
+    """Same recurrence; the halo travels by peer stores + flags (see PeerWindow)."""
+    import torch
+    p = self.plan
+    c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+    nscales, M = c.shape
+    nsig = int(x.shape[1])
+    n = p.n_local
+    if nsig not in self._windows:
+        self._windows[nsig] = PeerWindow(self, nsig)
+    win = self._windows[nsig]
+    bufs = win.bufs
+    base = self._seq
+    self._seq = base + M + 2
+    # entry barrier: nobody may write into a neighbour that is still in its previous call
+    win.signal(base + 1)
+    win.wait(base + 1)
+    xin = x.to(self.dtype)
+    bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
+    win.push(0, base + 2)                                # halo of T_0
+    r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
+    plan = self._tile_plan(nsig, nscales)
+    be = self.backend
+    cur, old = 0, 1
+    for k in range(1, M):
+        first = k == 1
+        ck = np.ascontiguousarray(c[:, k])
+        c0 = np.ascontiguousarray(c[:, 0])
+        coef = (2.0 / lmax, -1.0, 0.0) if first else (4.0 / lmax, -2.0, -1.0)
+        x_cur, x_new = bufs[cur], bufs[old]
+        win.wait(base + 1 + k)                           # halo of T_{k-1} has landed
+        be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
+                rows=(0, n))
+        if k < M - 1:
+            win.push(old, base + 2 + k)                  # halo of T_k
+        cur, old = old, cur
+    self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * bufs[0].element_size()
+    if local_order:
+        return r
+    out = torch.empty_like(r)
+    out[:, self.perm] = r
+    return out
+
+
+PartitionedCheby._cheby_op_p2p = _cheby_op_p2p
+
+
+class PeerWindow:
+    """State buffers + flags of one rank for one signal width, IPC-mapped by its neighbours.
+
+    One cudaMalloc'ed block: buf0 | buf1 | flags[P] (uint64) | push counter.  ``push``
+    stores this rank's boundary rows into the neighbours' halo rows and publishes a
+    sequence number; ``wait`` stalls the stream until the neighbours published it.
+    """
+
+    def __init__(self, op, nsig):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        p, self.op, self.nsig = op.plan, op, nsig
+        item = torch.empty((), dtype=op.dtype).element_size()
+        ext = p.n_local + p.n_halo
+        self.buf_bytes = ((ext * nsig * item + 255) // 256) * 256
+        flag_off = 2 * self.buf_bytes
+        total = flag_off + 8 * p.parts + 256
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(op.device):
+            nat.call("gsp_ipc_alloc", ctypes.c_size_t(total), ctypes.byref(ptr), handle)
+        self.base = int(ptr.value)
+        self.bufs = [_wrap(self.base + b * self.buf_bytes, (ext, nsig), op.dtype, op.device)
+                     for b in range(2)]
+        self.flags_ptr = self.base + flag_off
+        self.counter_ptr = self.flags_ptr + 8 * p.parts
+        # everybody learns everybody's handle, block size and halo layout
+        info = [None] * p.parts
+        dist.all_gather_object(info, (bytes(handle), int(p.n_local), p.recv_counts.tolist(),
+                                      int(self.buf_bytes)), group=op.group)
+        self.neighbors = [q for q in range(p.parts)
+                          if q != p.rank and (p.send_counts[q] > 0 or p.recv_counts[q] > 0)]
+        self.opened = {}
+        for q in self.neighbors:
+            qptr = ctypes.c_void_p()
+            hq = (ctypes.c_ubyte * 64).from_buffer_copy(info[q][0])
+            with torch.cuda.device(op.device):
+                nat.call("gsp_ipc_open", hq, ctypes.byref(qptr))
+            self.opened[q] = int(qptr.value)
+        dev = op.device
+        # destination row of every packed row: the slot the neighbour reserved for it
+        dst_peer, dst_row = [], []
+        for q in range(p.parts):
+            cnt = int(p.send_counts[q])
+            if cnt == 0:
+                continue
+            n_local_q, recv_q = info[q][1], info[q][2]
+            first = n_local_q + int(sum(recv_q[:p.rank]))     # q's halo slots are owner-ordered
+            dst_peer.append(np.full(cnt, q, dtype=np.int32))
+            dst_row.append(first + np.arange(cnt, dtype=np.int64))
+        cat = lambda parts, dt: torch.from_numpy(
+            np.concatenate(parts) if parts else np.zeros(0, dtype=dt)).to(dev)
+        self.dst_peer = cat(dst_peer, np.int32)
+        self.dst_row = cat(dst_row, np.int64)
+        self.src_row = op.send_idx
+        base_tab = np.zeros((2, p.parts), dtype=np.int64)
+        for q, qbase in self.opened.items():
+            for b in range(2):
+                base_tab[b, q] = qbase + b * info[q][3]
+        self.peer_base = torch.from_numpy(base_tab).to(dev)                  # pointers as int64
+        flag_tab = np.array([self.opened[q] + 2 * info[q][3] + 8 * p.rank for q in self.neighbors],
+                            dtype=np.int64)
+        self.peer_flags = torch.from_numpy(flag_tab).to(dev)
+        self.neighbor_ids = torch.from_numpy(np.asarray(self.neighbors, dtype=np.int32)).to(dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=op.group)
+
+    def push(self, b, value):
+        """Store my boundary rows of buffer b into the neighbours' buffer b; publish value."""
+        import ctypes
+        torch = nat.require_cuda()
+        op = self.op
+        with torch.cuda.device(op.device):
+            nat.call("gsp_halo_push_" + nat.suffix(op.dtype), nat.i64(self.src_row.numel()),
+                     self.src_row, self.dst_peer, self.dst_row, self.bufs[b],
+                     ctypes.c_void_p(self.peer_base[b].data_ptr()), nat.i64(self.nsig),
+                     self.peer_flags, nat.i32(len(self.neighbors)), nat.u64(value),
+                     ctypes.c_void_p(self.counter_ptr), nat.stream_ptr(op.device))
+
+    def signal(self, value):
+        """Publish value without moving data (entry barrier of a call)."""
+        import ctypes
+        torch = nat.require_cuda()
+        op = self.op
+        with torch.cuda.device(op.device):
+            nat.call("gsp_halo_push_" + nat.suffix(op.dtype), nat.i64(0), self.src_row,
+                     self.dst_peer, self.dst_row, self.bufs[0],
+                     ctypes.c_void_p(self.peer_base[0].data_ptr()), nat.i64(self.nsig),
+                     self.peer_flags, nat.i32(len(self.neighbors)), nat.u64(value),
+                     ctypes.c_void_p(self.counter_ptr), nat.stream_ptr(op.device))
+
+    def wait(self, value):
+        import ctypes
+        torch = nat.require_cuda()
+        with torch.cuda.device(self.op.device):
+            nat.call("gsp_halo_wait", ctypes.c_void_p(self.flags_ptr), self.neighbor_ids,
+                     nat.i32(len(self.neighbors)), nat.u64(value), nat.stream_ptr(self.op.device))
+
+    def close(self):
+        import ctypes
+        torch = nat.require_cuda()
+        torch.cuda.synchronize(self.op.device)
+        for qptr in self.opened.values():
+            nat.call("gsp_ipc_close", ctypes.c_void_p(qptr))
+        self.opened = {}
+        if self.base:
+            nat.call("gsp_ipc_free", ctypes.c_void_p(self.base))
+            self.base = 0
+
+
+class _RawCuda:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape),
+                                         "typestr": typestr, "version": 3, "strides": None}
+
+
+def _wrap(ptr, shape, dtype, device):
+    """A torch view (no copy, no ownership) of raw device memory."""
+    torch = nat.require_cuda()
+    typestr = {torch.float32: "<f4", torch.float64: "<f8"}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
 
 
 class _CudaBackend:

@@ -89,7 +89,10 @@ def main():
 
     if backend == "nccl":
         dtype = torch.float32
-        op = gd.PartitionedCheby(plan, dtype=dtype, overlap=(overlap == "1"))
+        if overlap == "p2p":
+            op = gd.PartitionedCheby(plan, dtype=dtype, exchange="p2p")
+        else:
+            op = gd.PartitionedCheby(plan, dtype=dtype, overlap=(overlap == "1"), exchange="nccl")
         xl = torch.from_numpy(x[lo:hi]).to(device=op.device, dtype=dtype)
         tol = 1e-5
     else:
@@ -108,8 +111,12 @@ def main():
         from pygsp_b200.graphs import DeviceCSR
         Ld = DeviceCSR.from_scipy(L, dtype, op.device)        # the same float32 values of L
         full = apx.cheby_op_device(Ld, lmax, c, torch.from_numpy(x).to(op.device, dtype))
-        mine = op.cheby_op(lmax, c, xl)
-        assert torch.equal(mine, full[:, lo:hi]), float((mine - full[:, lo:hi]).abs().max())
+        for _ in range(3):                                   # repeated calls reuse windows / flags
+            mine = op.cheby_op(lmax, c, xl)
+            assert torch.equal(mine, full[:, lo:hi]), float((mine - full[:, lo:hi]).abs().max())
+        x2 = torch.from_numpy(x[:, :32].copy()).to(op.device, dtype)      # another signal width
+        full2 = apx.cheby_op_device(Ld, lmax, c, x2)
+        assert torch.equal(op.cheby_op(lmax, c, x2[lo:hi].contiguous()), full2[:, lo:hi])
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok err=%.2e halo=%d boundary=%d/%d" % (rank, err, plan.n_halo, plan.n_true_boundary,

@@ -32,8 +32,15 @@ def test_partitioned_single_rank_matches_graph_path():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("overlap", [0, 1])
-def test_partitioned_two_ranks_nccl(overlap):
+@pytest.mark.parametrize("mode", ["0", "1", "p2p"])
+def test_partitioned_two_ranks(mode):
+    """NCCL all-to-all-v (unsplit / split + overlapped) and the NVLink peer-store exchange."""
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    run_world("nccl", 2, n=60000, nsig=64, nscales=2, order=20, overlap=overlap)
+    run_world("nccl", 2, n=60000, nsig=64, nscales=2, order=20, overlap=mode)
+
+
+def test_partitioned_four_ranks_p2p():
+    if _gpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    run_world("nccl", 4, n=120000, nsig=64, nscales=1, order=16, overlap="p2p")
