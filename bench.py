@@ -253,6 +253,7 @@ def build_partitioned(gsp, wl, rank, world, torch, dist):
     ov = os.environ.get("GSPB200_OVERLAP")          # default: decided from the halo size
     op = gd.PartitionedCheby(plan, dtype=torch.float32, overlap=None if ov is None else ov != "0",
                              exchange=os.environ.get("GSPB200_EXCHANGE"))   # default: p2p
+    op.fuse_halo = os.environ.get("GSPB200_FUSE_HALO", "1") != "0"
     return op, float(bound.item()), int(L_rows.nnz)
 
 

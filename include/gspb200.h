@@ -66,6 +66,40 @@ typedef struct gsp_tile_plan {
 int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales,
                         gsp_tile_plan* plan_host_out, void* stream);
 
+/* Halo exchange fused into the tiled float32 step (vertex-partitioned path): the
+ * kernel first waits until flags[wait_ids[q]] >= wait_value (the neighbours have stored
+ * x_cur's halo rows into this GPU), stores every row < n_push_rows of x_new into
+ * peer_base[push_peer[e]][push_row[e], :] for e in [push_ptr[row], push_ptr[row+1])
+ * from its epilogue (peer stores over NVLink), and, when the last boundary tile is
+ * done, writes publish_value to every peer_flags[q].  All pointers are device pointers;
+ * the struct itself is a host struct.  n_push_tiles is filled in by the library. */
+typedef struct gsp_halo_fusion {
+  int64_t n_push_rows;
+  int64_t n_push_tiles;
+  const int32_t* push_ptr;
+  const int32_t* push_peer;
+  const int64_t* push_row;
+  void* const* peer_base;          /* float* const*  : peers' x_new buffers */
+  uint64_t* const* peer_flags;     /* my slot in each neighbour's flag array */
+  uint64_t* push_counter;          /* one zero-initialised device uint64 */
+  const uint64_t* wait_flags;      /* my own flag array */
+  const int32_t* wait_ids;         /* neighbour ranks to wait for */
+  uint64_t publish_value;
+  uint64_t wait_value;
+  int32_t n_neighbors;
+  int32_t n_wait;
+} gsp_halo_fusion;
+
+/* One fused step on the whole local row block with the halo exchange folded in
+ * (float32, tiled kernel required: returns -3 when no tile plan applies). */
+int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_t* indptr,
+                            const int32_t* indices, const float* data, const float* x_cur,
+                            const float* x_old, float* x_new, float* r, int64_t r_rows,
+                            int64_t nsig, int nscales, const double* ck_host,
+                            const double* c0_host, double alpha, double beta, double gamma,
+                            const gsp_tile_plan* plan_host, const gsp_halo_fusion* halo_host,
+                            void* stream);
+
 #define GSPB200_DECLARE_CHEBY_API(SUF, T)                                                         \
   int gsp_cheby_op_##SUF(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,   \
                          const T* data, double lmax, const double* coeffs_host, int nscales,      \

@@ -30,6 +30,17 @@ class TilePlan(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class HaloFusion(ctypes.Structure):
+    """Mirror of ``gsp_halo_fusion`` (include/gspb200.h)."""
+    _fields_ = [("n_push_rows", ctypes.c_int64), ("n_push_tiles", ctypes.c_int64),
+                ("push_ptr", ctypes.c_void_p), ("push_peer", ctypes.c_void_p),
+                ("push_row", ctypes.c_void_p), ("peer_base", ctypes.c_void_p),
+                ("peer_flags", ctypes.c_void_p), ("push_counter", ctypes.c_void_p),
+                ("wait_flags", ctypes.c_void_p), ("wait_ids", ctypes.c_void_p),
+                ("publish_value", ctypes.c_uint64), ("wait_value", ctypes.c_uint64),
+                ("n_neighbors", ctypes.c_int32), ("n_wait", ctypes.c_int32)]
+
+
 def header_symbols():
     """Every function name include/gspb200.h declares (macro-expanded)."""
     text = open(_HEADER).read()
@@ -67,7 +78,7 @@ def _arg(a):
     """torch tensor -> device pointer; None -> NULL; numpy -> host pointer."""
     if a is None:
         return ctypes.c_void_p(0)
-    if isinstance(a, TilePlan):
+    if isinstance(a, (TilePlan, HaloFusion)):
         return ctypes.byref(a)
     if hasattr(a, "data_ptr"):
         return ctypes.c_void_p(a.data_ptr())

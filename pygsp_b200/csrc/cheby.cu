@@ -30,8 +30,8 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const int32_t* indices, const float* vals, const float* x_cur,
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
-                         double gamma, const gsp_tile_plan& plan, int64_t* rows_done,
-                         cudaStream_t st);
+                         double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
+                         int64_t* rows_done, cudaStream_t st);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -268,8 +268,8 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
   int64_t done = 0;
   if (tiled) {
     int rc = cheby_step_tiled_f32(first, rb, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
-                                  r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, &done,
-                                  st);
+                                  r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, nullptr,
+                                  &done, st);
     if (rc != GSP_OK) return rc;
   }
   return cheby_step<float>(first, rb + done, re, indptr, indices, vals, x_cur, x_old, x_new, r,
@@ -369,5 +369,27 @@ extern "C" {
 
 GSP_CHEBY_API(f32, float)
 GSP_CHEBY_API(f64, double)
+
+int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_t* indptr,
+                            const int32_t* indices, const float* data, const float* x_cur,
+                            const float* x_old, float* x_new, float* r, int64_t r_rows,
+                            int64_t nsig, int nscales, const double* ck_host,
+                            const double* c0_host, double alpha, double beta, double gamma,
+                            const gsp_tile_plan* plan_host, const gsp_halo_fusion* halo_host,
+                            void* stream) {
+  if (!(plan_host && plan_host->rows_per_tile > 0 && halo_host))
+    return gsp::fail(GSP_ERR_UNSUPPORTED, "fused halo step needs a tile plan (%s)", "plan");
+  GSP_REQUIRE(nscales <= gsp::kMaxScales, "too many filters for the fused step");
+  int64_t done = 0;
+  int rc = gsp::cheby_step_tiled_f32(first != 0, 0, n_rows, nnz, indptr, indices, data, x_cur,
+                                     x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
+                                     c0_host, alpha, beta, gamma, *plan_host, halo_host, &done,
+                                     gsp::as_stream(stream));
+  if (rc != GSP_OK) return rc;
+  // remainder rows (< rows_per_tile, interior by construction) with the row-group kernel
+  return gsp::cheby_step<float>(first != 0, done, n_rows, indptr, indices, data, x_cur, x_old,
+                                x_new, r, r_rows, (int)nsig, nscales, ck_host, c0_host, alpha,
+                                beta, gamma, gsp::as_stream(stream));
+}
 
 }  // extern "C"

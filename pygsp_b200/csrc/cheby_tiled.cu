@@ -47,6 +47,7 @@ struct TileArgs {
   float alpha, beta, gamma;
   float half_c0[kTiledMaxScales];
   float ck[kTiledMaxScales];
+  gsp_halo_fusion halo;   // all zero when the step does not exchange a halo
 };
 
 // ----------------------------------------------------------------- PTX helpers
@@ -127,6 +128,16 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Halo of x_cur: written by the neighbours' previous step straight into this
+  // GPU's memory; they published `wait_value` after their stores were fenced.
+  if (a.halo.n_wait > 0 && int(threadIdx.x) < a.halo.n_wait) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.halo.wait_flags) +
+                                  a.halo.wait_ids[threadIdx.x];
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+    } while (seen < a.halo.wait_value);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -215,6 +226,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
     const int a0 = sm_ptr[R + 4];
     const int64_t r0 = a.row_begin + tile * R;
+    const bool push_tile = tile < a.halo.n_push_tiles;      // warp-uniform
     const float* __restrict__ xc_tile = xg + r0 * NS;
     float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
     float* __restrict__ r_tile = a.r + r0 * NS + c0;
@@ -280,6 +292,18 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
         xn.w = fmaf(gamma, xo.w, xn.w);
       }
       stcs_f4(xn_tile + off, xn);
+      if (push_tile) {
+        // fused halo push: this row's new value goes straight into the halo rows of
+        // the neighbours that reference it (peer stores over NVLink)
+        const int64_t lrow = tile * R + lr;
+        if (lrow < a.halo.n_push_rows) {
+          for (int e = a.halo.push_ptr[lrow]; e < a.halo.push_ptr[lrow + 1]; ++e) {
+            float* dst = reinterpret_cast<float* const*>(a.halo.peer_base)[a.halo.push_peer[e]] +
+                         a.halo.push_row[e] * NS + c0;
+            *reinterpret_cast<float4*>(dst) = xn;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
         if (NSC < 0 && i >= nscales) break;
@@ -299,6 +323,27 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           rv.w = fmaf(ck, xn.w, rv.w);
         }
         stcs_f4(r_tile + i * r_stride + off, rv);
+      }
+    }
+    if (push_tile) {
+      // all boundary tiles done (every warp of every CTA checks in once per tile):
+      // publish the step to the neighbours
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned long long want =
+            (unsigned long long)a.halo.n_push_tiles * (unsigned long long)NW;
+        const unsigned long long prev = atomicAdd(
+            reinterpret_cast<unsigned long long*>(a.halo.push_counter), 1ull);
+        if (prev + 1 == want) {
+          *reinterpret_cast<volatile unsigned long long*>(a.halo.push_counter) = 0ull;
+          __threadfence_system();
+          for (int q = 0; q < a.halo.n_neighbors; ++q)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(
+                             reinterpret_cast<unsigned long long* const*>(a.halo.peer_flags)[q]),
+                         "l"((unsigned long long)a.halo.publish_value)
+                         : "memory");
+        }
       }
     }
     __syncwarp();
@@ -413,9 +458,18 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const int32_t* indices, const float* vals, const float* x_cur,
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
-                         double gamma, const gsp_tile_plan& plan, int64_t* rows_done,
-                         cudaStream_t st) {
+                         double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
+                         int64_t* rows_done, cudaStream_t st) {
   TileArgs a;
+  memset(&a.halo, 0, sizeof(a.halo));
+  if (halo) {
+    a.halo = *halo;
+    GSP_REQUIRE(rb == 0, "fused halo push needs the whole row block in one launch");
+    a.halo.n_push_tiles = ceil_div(halo->n_push_rows, plan.rows_per_tile);
+    GSP_REQUIRE(a.halo.n_push_tiles <= (re - rb) / plan.rows_per_tile,
+                "boundary rows must lie inside the full tiles");
+    GSP_REQUIRE(halo->n_wait <= 32, "at most 32 neighbours");
+  }
   a.row_begin = rb;
   a.n_tiles = (re - rb) / plan.rows_per_tile;
   *rows_done = a.n_tiles * plan.rows_per_tile;

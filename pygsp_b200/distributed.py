@@ -146,6 +146,7 @@ class PartitionedCheby:
         # NVLink peer memory, flags order the steps (csrc/halo.cu); 'nccl': pack +
         # all_to_all_single.  Default: p2p on GPUs, collective on the CPU test backend.
         self.exchange = exchange
+        self.fuse_halo = True
         self._windows = {}
         self._seq = 0
         self.backend = backend if backend is not None else _CudaBackend(device)
@@ -268,6 +269,11 @@ def _cheby_op_p2p(self, lmax, c, x, local_order):
     r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
     plan = self._tile_plan(nsig, nscales)
     be = self.backend
+    # Fused form: the step kernel itself waits for the halo of T_{k-1}, stores the
+    # boundary rows of T_k into the neighbours from its epilogue (boundary tiles run
+    # first) and publishes the step -- no pack kernel, no collective, no extra launch.
+    fused = (self.fuse_halo and plan is not None and self.dtype == torch.float32 and
+             nscales <= 16 and win.n_push_rows <= (n // plan.rows_per_tile) * plan.rows_per_tile)
     cur, old = 0, 1
     for k in range(1, M):
         first = k == 1
@@ -275,11 +281,16 @@ def _cheby_op_p2p(self, lmax, c, x, local_order):
         c0 = np.ascontiguousarray(c[:, 0])
         coef = (2.0 / lmax, -1.0, 0.0) if first else (4.0 / lmax, -2.0, -1.0)
         x_cur, x_new = bufs[cur], bufs[old]
-        win.wait(base + 1 + k)                           # halo of T_{k-1} has landed
-        be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
-                rows=(0, n))
-        if k < M - 1:
-            win.push(old, base + 2 + k)                  # halo of T_k
+        if fused:
+            halo = win.fusion(old, base + 1 + k, base + 2 + k, push=k < M - 1)
+            be.step_halo(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
+                         halo)
+        else:
+            win.wait(base + 1 + k)                       # halo of T_{k-1} has landed
+            be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
+                    rows=(0, n))
+            if k < M - 1:
+                win.push(old, base + 2 + k)              # halo of T_k
         cur, old = old, cur
     self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * bufs[0].element_size()
     if local_order:
@@ -357,6 +368,16 @@ class PeerWindow:
                             dtype=np.int64)
         self.peer_flags = torch.from_numpy(flag_tab).to(dev)
         self.neighbor_ids = torch.from_numpy(np.asarray(self.neighbors, dtype=np.int32)).to(dev)
+        # the same send list as a CSR over the local rows, for the fused epilogue push
+        src = p.send_idx
+        order = np.argsort(src, kind="stable")
+        self.n_push_rows = int(src.max()) + 1 if src.size else 0
+        ptr = np.zeros(self.n_push_rows + 1, dtype=np.int64)
+        np.add.at(ptr, src + 1, 1)
+        self.push_ptr = torch.from_numpy(np.cumsum(ptr).astype(np.int32)).to(dev)
+        self.push_peer = self.dst_peer[torch.from_numpy(order).to(dev)].contiguous()
+        self.push_row = self.dst_row[torch.from_numpy(order).to(dev)].contiguous()
+        self.fused_counter_ptr = self.counter_ptr + 8
         torch.cuda.synchronize(dev)
         dist.barrier(group=op.group)
 
@@ -371,6 +392,24 @@ class PeerWindow:
                      ctypes.c_void_p(self.peer_base[b].data_ptr()), nat.i64(self.nsig),
                      self.peer_flags, nat.i32(len(self.neighbors)), nat.u64(value),
                      ctypes.c_void_p(self.counter_ptr), nat.stream_ptr(op.device))
+
+    def fusion(self, b, wait_value, publish_value, push):
+        """The ``gsp_halo_fusion`` block of one step whose x_new is buffer b."""
+        h = nat.HaloFusion()
+        h.n_push_rows = self.n_push_rows if push else 0
+        h.push_ptr = self.push_ptr.data_ptr()
+        h.push_peer = self.push_peer.data_ptr()
+        h.push_row = self.push_row.data_ptr()
+        h.peer_base = self.peer_base[b].data_ptr()
+        h.peer_flags = self.peer_flags.data_ptr()
+        h.push_counter = self.fused_counter_ptr
+        h.wait_flags = self.flags_ptr
+        h.wait_ids = self.neighbor_ids.data_ptr()
+        h.publish_value = publish_value
+        h.wait_value = wait_value
+        h.n_neighbors = len(self.neighbors)
+        h.n_wait = len(self.neighbors)
+        return h
 
     def signal(self, value):
         """Publish value without moving data (entry barrier of a call)."""
@@ -455,6 +494,16 @@ class _CudaBackend:
                      op.indices, op.data, x_cur, None if first else x_old, x_new, r,
                      nat.i64(op.plan.n_local), nat.i64(nsig), nat.i32(nscales), ck, c0,
                      nat.f64(coef[0]), nat.f64(coef[1]), nat.f64(coef[2]), plan,
+                     nat.stream_ptr(self.device))
+
+    def step_halo(self, op, first, x_cur, x_old, x_new, r, nsig, nscales, ck, c0, coef, plan, halo):
+        torch = nat.require_cuda()
+        with torch.cuda.device(self.device):
+            nat.call("gsp_cheby_step_halo_f32", nat.i32(1 if first else 0),
+                     nat.i64(op.plan.n_local), nat.i64(op.plan.nnz), op.indptr, op.indices,
+                     op.data, x_cur, None if first else x_old, x_new, r,
+                     nat.i64(op.plan.n_local), nat.i64(nsig), nat.i32(nscales), ck, c0,
+                     nat.f64(coef[0]), nat.f64(coef[1]), nat.f64(coef[2]), plan, halo,
                      nat.stream_ptr(self.device))
 
     def fork_exchange(self, fn):

@@ -89,8 +89,9 @@ def main():
 
     if backend == "nccl":
         dtype = torch.float32
-        if overlap == "p2p":
+        if overlap in ("p2p", "p2p_unfused"):
             op = gd.PartitionedCheby(plan, dtype=dtype, exchange="p2p")
+            op.fuse_halo = overlap == "p2p"
         else:
             op = gd.PartitionedCheby(plan, dtype=dtype, overlap=(overlap == "1"), exchange="nccl")
         xl = torch.from_numpy(x[lo:hi]).to(device=op.device, dtype=dtype)

@@ -32,7 +32,7 @@ def test_partitioned_single_rank_matches_graph_path():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "p2p"])
+@pytest.mark.parametrize("mode", ["0", "1", "p2p", "p2p_unfused"])
 def test_partitioned_two_ranks(mode):
     """NCCL all-to-all-v (unsplit / split + overlapped) and the NVLink peer-store exchange."""
     if _gpus() < 2:
