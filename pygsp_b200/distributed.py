@@ -245,62 +245,58 @@ class PartitionedCheby:
         out[:, self.perm] = r
         return out
 
-
-def _cheby_op_p2p(self, lmax, c, x, local_order):
-    """Same recurrence; the halo travels by peer stores + flags (see PeerWindow)."""
-    import torch
-    p = self.plan
-    c = np.atleast_2d(np.asarray(c, dtype=np.float64))
-    nscales, M = c.shape
-    nsig = int(x.shape[1])
-    n = p.n_local
-    if nsig not in self._windows:
-        self._windows[nsig] = PeerWindow(self, nsig)
-    win = self._windows[nsig]
-    bufs = win.bufs
-    base = self._seq
-    self._seq = base + M + 2
-    # entry barrier: nobody may write into a neighbour that is still in its previous call
-    win.signal(base + 1)
-    win.wait(base + 1)
-    xin = x.to(self.dtype)
-    bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
-    win.push(0, base + 2)                                # halo of T_0
-    r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
-    plan = self._tile_plan(nsig, nscales)
-    be = self.backend
-    # Fused form: the step kernel itself waits for the halo of T_{k-1}, stores the
-    # boundary rows of T_k into the neighbours from its epilogue (boundary tiles run
-    # first) and publishes the step -- no pack kernel, no collective, no extra launch.
-    fused = (self.fuse_halo and plan is not None and self.dtype == torch.float32 and
-             nscales <= 16 and win.n_push_rows <= (n // plan.rows_per_tile) * plan.rows_per_tile)
-    cur, old = 0, 1
-    for k in range(1, M):
-        first = k == 1
-        ck = np.ascontiguousarray(c[:, k])
-        c0 = np.ascontiguousarray(c[:, 0])
-        coef = (2.0 / lmax, -1.0, 0.0) if first else (4.0 / lmax, -2.0, -1.0)
-        x_cur, x_new = bufs[cur], bufs[old]
-        if fused:
-            halo = win.fusion(old, base + 1 + k, base + 2 + k, push=k < M - 1)
-            be.step_halo(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
-                         halo)
-        else:
-            win.wait(base + 1 + k)                       # halo of T_{k-1} has landed
-            be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
-                    rows=(0, n))
-            if k < M - 1:
-                win.push(old, base + 2 + k)              # halo of T_k
-        cur, old = old, cur
-    self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * bufs[0].element_size()
-    if local_order:
-        return r
-    out = torch.empty_like(r)
-    out[:, self.perm] = r
-    return out
-
-
-PartitionedCheby._cheby_op_p2p = _cheby_op_p2p
+    def _cheby_op_p2p(self, lmax, c, x, local_order):
+        """Same recurrence; the halo travels by peer stores + flags (see PeerWindow)."""
+        import torch
+        p = self.plan
+        c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+        nscales, M = c.shape
+        nsig = int(x.shape[1])
+        n = p.n_local
+        if nsig not in self._windows:
+            self._windows[nsig] = PeerWindow(self, nsig)
+        win = self._windows[nsig]
+        bufs = win.bufs
+        base = self._seq
+        self._seq = base + M + 2
+        # entry barrier: nobody may write into a neighbour that is still in its previous call
+        win.signal(base + 1)
+        win.wait(base + 1)
+        xin = x.to(self.dtype)
+        bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
+        win.push(0, base + 2)                                # halo of T_0
+        r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
+        plan = self._tile_plan(nsig, nscales)
+        be = self.backend
+        # Fused form: the step kernel itself waits for the halo of T_{k-1}, stores the
+        # boundary rows of T_k into the neighbours from its epilogue (boundary tiles run
+        # first) and publishes the step -- no pack kernel, no collective, no extra launch.
+        fused = (self.fuse_halo and plan is not None and self.dtype == torch.float32 and
+                 nscales <= 16 and win.n_push_rows <= (n // plan.rows_per_tile) * plan.rows_per_tile)
+        cur, old = 0, 1
+        for k in range(1, M):
+            first = k == 1
+            ck = np.ascontiguousarray(c[:, k])
+            c0 = np.ascontiguousarray(c[:, 0])
+            coef = (2.0 / lmax, -1.0, 0.0) if first else (4.0 / lmax, -2.0, -1.0)
+            x_cur, x_new = bufs[cur], bufs[old]
+            if fused:
+                halo = win.fusion(old, base + 1 + k, base + 2 + k, push=k < M - 1)
+                be.step_halo(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
+                             halo)
+            else:
+                win.wait(base + 1 + k)                       # halo of T_{k-1} has landed
+                be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
+                        rows=(0, n))
+                if k < M - 1:
+                    win.push(old, base + 2 + k)              # halo of T_k
+            cur, old = old, cur
+        self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * bufs[0].element_size()
+        if local_order:
+            return r
+        out = torch.empty_like(r)
+        out[:, self.perm] = r
+        return out
 
 
 class PeerWindow:

@@ -150,3 +150,32 @@ def cheby_rect(G, bounds, signal, **kwargs):
     c[0] = 2.0 * (b1 - b2) / np.pi
     c[1:] = 2.0 / (k * np.pi) * (np.sin(k * b1) - np.sin(k * b2))
     return cheby_op(G, c, signal)
+
+
+def compute_jackson_cheby_coeff(filter_bounds, delta_lambda, m):
+    r"""Chebyshev and Jackson-damped coefficients of an ideal band-pass.
+
+    Reference: approximations.py:166-225.  For the band [a, b] inside
+    [lambda_min, lambda_max], mapped to [-1, 1]: ``ch[0] = 2/pi (acos a' - acos b')``,
+    ``ch[i] = 2/(pi i) (sin(i acos a') - sin(i acos b'))``; the Jackson factors
+    ``g_i = ((1 - i/(m+2)) sin(t) cos(i t) + cos(t) sin(i t)/(m+2)) / sin(t)``,
+    ``t = pi/(m+2)``, damp the Gibbs oscillations.  Returns ``(ch, ch * g)``; either
+    feeds :func:`cheby_op` directly (host code, m+1 numbers).  Unlike the reference
+    the caller's ``filter_bounds`` list is not modified.
+    """
+    lo, hi = float(delta_lambda[0]), float(delta_lambda[1])
+    a, b = float(filter_bounds[0]), float(filter_bounds[1])
+    if lo > a or hi < b:
+        raise ValueError("Bounds of the filter are out of the lambda values")
+    if lo > hi:
+        raise ValueError("lambda_min is greater than lambda_max")
+    half, mid = (hi - lo) / 2, (hi + lo) / 2
+    ta, tb = np.arccos((a - mid) / half), np.arccos((b - mid) / half)
+    i = np.arange(1, m + 1)
+    ch = np.empty(m + 1)
+    ch[0] = 2 / np.pi * (ta - tb)
+    ch[1:] = 2 / (np.pi * i) * (np.sin(i * ta) - np.sin(i * tb))
+    j = np.arange(m + 1)
+    t = np.pi / (m + 2)
+    damp = ((1 - j / (m + 2)) * np.sin(t) * np.cos(j * t) + np.cos(t) * np.sin(j * t) / (m + 2)) / np.sin(t)
+    return ch, ch * damp

@@ -2,4 +2,4 @@
 from .csr import DeviceCSR  # noqa: F401
 from .graph import Graph  # noqa: F401
 from .generators import (Grid2d, Logo, NNGraph, Ring, Sensor, SensorStrips,  # noqa: F401
-                         laplacian_rows, morton_order)
+                         StochasticBlockModel, laplacian_rows, morton_order, sbm_adjacency)

@@ -218,3 +218,89 @@ def laplacian_rows(W_rows, row_offset):
     L.eliminate_zeros()
     L.sort_indices()
     return L, dw
+
+
+def sbm_adjacency(N=1024, k=5, z=None, p=0.7, q=None, seed=None):
+    r"""Adjacency of an undirected, loop-free stochastic block model, vectorised.
+
+    Same model as pygsp/graphs/stochasticblockmodel.py:61-144 with its defaults
+    (``z = sort(rng.integers(0, k, N))``, edge (i, j), i != j, present with probability
+    ``M[z_i, z_j]``, ``M`` = ``q`` off the diagonal and ``p`` on it, unit weights).  The
+    reference draws one uniform per vertex pair in a Python loop (N^2 iterations: unusable
+    beyond N ~ 3e3); here every block pair draws its edge COUNT from the binomial law and then
+    that many distinct pairs uniformly -- the same distribution, O(edges) work.  The
+    random stream necessarily differs from the reference's, so parity is statistical
+    (tests/test_generators_cpu.py).
+    """
+    rng = np.random.default_rng(seed)
+    if z is None:
+        z = np.sort(rng.integers(0, k, N))
+    z = np.asarray(z)
+    pv = np.asarray(p, dtype=np.float64)
+    pv = pv * np.ones(k) if pv.size == 1 else pv
+    if pv.shape != (k,):
+        raise ValueError("Optional parameter p is neither a scalar nor a vector of length k.")
+    if q is None:
+        q = 0.3 / k
+    M = np.asarray(q, dtype=np.float64)
+    M = M * np.ones((k, k)) if M.size == 1 else M.copy()
+    if M.shape != (k, k):
+        raise ValueError("Optional parameter q is neither a scalar nor a matrix of size k x k.")
+    M.flat[::k + 1] = pv
+    if (M < 0).any() or (M > 1).any():
+        raise ValueError("Probabilities should be in [0, 1].")
+    if np.any(np.diff(z) < 0):
+        raise ValueError("z must be sorted (blocks contiguous) for the vectorised sampler")
+    start = np.searchsorted(z, np.arange(k), side="left")
+    size = np.searchsorted(z, np.arange(k), side="right") - start
+
+    def distinct(n_pairs, m):
+        """m distinct integers from range(n_pairs), uniformly."""
+        if m == 0:
+            return np.zeros(0, dtype=np.int64)
+        if m > n_pairs // 3:
+            return rng.choice(n_pairs, size=m, replace=False).astype(np.int64)
+        got = np.unique(rng.integers(0, n_pairs, int(m * 1.05) + 16))
+        while got.size < m:
+            got = np.unique(np.concatenate([got, rng.integers(0, n_pairs, m - got.size + 16)]))
+        return rng.permutation(got)[:m]
+
+    rows, cols = [], []
+    for a in range(k):
+        for b in range(a + 1):
+            if a == b:
+                n_pairs = int(size[a]) * (int(size[a]) - 1) // 2
+            else:
+                n_pairs = int(size[a]) * int(size[b])
+            if n_pairs == 0 or M[a, b] == 0:
+                continue
+            idx = distinct(n_pairs, int(rng.binomial(n_pairs, M[a, b])))
+            if a == b:            # index -> (i > j) of the strict lower triangle
+                i = np.floor((1 + np.sqrt(1 + 8 * idx.astype(np.float64))) / 2).astype(np.int64)
+                i -= (i * (i - 1) // 2 > idx)
+                i += ((i + 1) * i // 2 <= idx)
+                j = idx - i * (i - 1) // 2
+            else:
+                i, j = idx // int(size[b]), idx % int(size[b])
+            rows.append(start[a] + i)
+            cols.append(start[b] + j)
+    if rows:
+        r = np.concatenate(rows)
+        c = np.concatenate(cols)
+    else:
+        r = c = np.zeros(0, dtype=np.int64)
+    W = sparse.coo_matrix((np.ones(2 * r.size), (np.concatenate([r, c]), np.concatenate([c, r]))),
+                          shape=(N, N)).tocsr()
+    W.sort_indices()
+    return W, z
+
+
+class StochasticBlockModel(Graph):
+    r"""Stochastic block model graph (undirected, no self-loops); see :func:`sbm_adjacency`."""
+
+    def __init__(self, N=1024, k=5, z=None, p=0.7, q=None, seed=None, **kwargs):
+        self.k, self.p, self.q, self.seed = k, p, q, seed
+        W, self.z = sbm_adjacency(N, k, z, p, q, seed)
+        self.info = {"node_com": self.z, "comm_sizes": np.bincount(self.z, minlength=k),
+                     "world_rad": np.sqrt(N)}
+        super().__init__(W, **kwargs)

@@ -71,3 +71,16 @@ def test_morton_order_is_a_permutation():
     d = np.linalg.norm(np.diff(pts[perm], axis=0), axis=1).mean()
     assert d < 0.1
     assert sorted(morton_order(np.random.default_rng(1).uniform(size=(500, 3))).tolist()) == list(range(500))
+
+
+def test_jackson_coefficients(golden):
+    """approximations.py:166-225, golden from PyGSP."""
+    from pygsp_b200 import filters
+    g = golden("jackson")
+    bounds = [float(g["bounds"][0]), float(g["bounds"][1])]
+    ch, jch = filters.compute_jackson_cheby_coeff(bounds, list(g["lam"]), int(g["m"]))
+    np.testing.assert_allclose(ch, g["ch"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(jch, g["jch"], rtol=1e-12, atol=1e-15)
+    assert bounds == [1.0, 4.0]                      # the caller's list is left alone
+    with pytest.raises(ValueError):
+        filters.compute_jackson_cheby_coeff([1.0, 20.0], [0.0, 13.9], 10)

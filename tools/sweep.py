@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--nsig", type=int, default=64)
+    ap.add_argument("--nsigs", default=None, help="comma list: run every config for each width")
     ap.add_argument("--nscales", type=int, default=1)
     ap.add_argument("--order", type=int, default=30)
     ap.add_argument("--steps", type=int, default=5)
@@ -48,12 +49,17 @@ def main():
     c = np.atleast_2d(np.array(gsp.filters.compute_cheby_coeff(filt, m=a.order)))
     print(json.dumps({"graph": a.graph, "N": G.N, "nnz_L": G.L.nnz, "lmax": G.lmax,
                       "lanczos_steps": G._lanczos_steps}), flush=True)
-    x = torch.randn(a.n, a.nsig, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
-    _, _, b_call = bench.algorithmic_bytes(a.n, G.L.nnz, a.nsig, a.nscales, a.order)
     peak, _ = bench.measured_peak()
-    ref = None
     results = []
-    for cfg in a.configs or ["KERNEL=rowgroup"]:
+    widths = [int(v) for v in a.nsigs.split(",")] if a.nsigs else [a.nsig]
+    runs = [(w, cfg) for w in widths for cfg in (a.configs or ["KERNEL=rowgroup"])]
+    ref, last_w = None, None
+    for a.nsig, cfg in runs:
+        if a.nsig != last_w:
+            x = torch.randn(a.n, a.nsig, device="cuda",
+                            generator=torch.Generator("cuda").manual_seed(0))
+            _, _, b_call = bench.algorithmic_bytes(a.n, G.L.nnz, a.nsig, a.nscales, a.order)
+            ref, last_w = None, a.nsig
         for k in [k for k in os.environ if k.startswith("GSPB200_")]:
             del os.environ[k]
         for kv in cfg.split(","):
@@ -75,7 +81,8 @@ def main():
                 ref = y.clone()
             err = float((y - ref).abs().max() / ref.abs().max())
             plan = G.L.tile_plan(a.nsig, a.nscales)
-            row = {"cfg": cfg, "ms": round(ms, 3), "frac": round(b_call / ms / 1e6 / peak, 4),
+            row = {"cfg": cfg, "nsig": a.nsig, "ms": round(ms, 3),
+                   "frac": round(b_call / ms / 1e6 / peak, 4),
                    "units_per_s": a.n * a.nsig * a.order / ms * 1e3,
                    "maxdiff_vs_first": err, "plan": plan.as_dict() if plan else None}
         except Exception as exc:  # keep sweeping
