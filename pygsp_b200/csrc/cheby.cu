@@ -31,7 +31,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
-                         int64_t* rows_done, cudaStream_t st);
+                         int64_t* rows_done, cudaStream_t st, bool add_source = false);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -43,6 +43,9 @@ struct StepCoef {
   T alpha, beta, gamma;
   T half_c0[kMaxScales];   // c[i,0]/2 (first step only)
   T ck[kMaxScales];        // c[i,k]
+  // Clenshaw form (single filter): `r` is a read-only source block s and the step
+  // is x_new += ck[0] * s; nothing is accumulated into r.
+  int add_source;
 };
 
 template <typename T, int VEC, int G, bool FIRST, bool SPMM>
@@ -114,6 +117,13 @@ cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
       T t = fma(coef.alpha, acc.v[v], coef.beta * xc.v[v]);
       if (!FIRST) t = fma(coef.gamma, xo.v[v], t);
       xn.v[v] = t;
+    }
+    if (coef.add_source) {
+      const Vec<T, VEC> sv = load_vec_stream<T, VEC>(r + row * nsig + c0);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) xn.v[v] = fma(coef.ck[0], sv.v[v], xn.v[v]);
+      store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
+      continue;
     }
     store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
 
@@ -201,7 +211,8 @@ template <typename T>
 int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
                const int32_t* indices, const T* vals, const T* x_cur, const T* x_old,
                T* x_new, T* r, int64_t r_rows, int nsig, int nscales, const double* ck,
-               const double* c0, double alpha, double beta, double gamma, cudaStream_t st) {
+               const double* c0, double alpha, double beta, double gamma, cudaStream_t st,
+               bool add_source) {
   constexpr int MV = MaxVec<T>::value;
   const bool vec_ok = (nsig % MV == 0) && aligned16(x_cur) && aligned16(x_new) &&
                       aligned16(r) && (first || aligned16(x_old));
@@ -211,6 +222,7 @@ int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
     coef.alpha = T(alpha);
     coef.beta = T(beta);
     coef.gamma = T(gamma);
+    coef.add_source = add_source ? 1 : 0;
     for (int i = 0; i < kMaxScales; ++i) {
       coef.ck[i] = i < ns ? T(ck[s0 + i]) : T(0);
       coef.half_c0[i] = (first && i < ns) ? T(0.5 * c0[s0 + i]) : T(0);
@@ -247,9 +259,9 @@ static int cheby_step_planned(const gsp_tile_plan* plan, int64_t nnz, bool first
                               const T* vals, const T* x_cur, const T* x_old, T* x_new, T* r,
                               int64_t r_rows, int nsig, int nscales, const double* ck,
                               const double* c0, double alpha, double beta, double gamma,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool add_source = false) {
   return cheby_step<T>(first, rb, re, indptr, indices, vals, x_cur, x_old, x_new, r, r_rows, nsig,
-                       nscales, ck, c0, alpha, beta, gamma, st);
+                       nscales, ck, c0, alpha, beta, gamma, st, add_source);
 }
 
 // float32 with a tile plan: TMA-tiled kernel on the full tiles of [rb, re), the
@@ -260,7 +272,7 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
                               const float* vals, const float* x_cur, const float* x_old,
                               float* x_new, float* r, int64_t r_rows, int nsig, int nscales,
                               const double* ck, const double* c0, double alpha, double beta,
-                              double gamma, cudaStream_t st) {
+                              double gamma, cudaStream_t st, bool add_source) {
   const bool tiled = plan && plan->rows_per_tile > 0 && rb % 4 == 0 && nscales <= kMaxScales &&
                      aligned16(indptr) && aligned16(indices) && aligned16(vals) &&
                      aligned16(x_cur) && aligned16(x_new) && aligned16(r) &&
@@ -269,11 +281,11 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
   if (tiled) {
     int rc = cheby_step_tiled_f32(first, rb, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
                                   r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, nullptr,
-                                  &done, st);
+                                  &done, st, add_source);
     if (rc != GSP_OK) return rc;
   }
   return cheby_step<float>(first, rb + done, re, indptr, indices, vals, x_cur, x_old, x_new, r,
-                           r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st);
+                           r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st, add_source);
 }
 
 // Full operator (approximations.py:58-114): K = m-1 fused steps on `stream`.
@@ -315,6 +327,61 @@ int cheby_op(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indic
   return GSP_OK;
 }
 
+// Single-filter Chebyshev sum by Clenshaw's recurrence:
+//   b_k = c_k x + 2 Lt b_{k+1} - b_{k+2},  Lt = (2/lmax) L - I,  b_{K+1} = b_{K+2} = 0
+//   p(L) x = c_0/2 x + Lt b_1 - b_2
+// Same K SpMMs as the forward form, but no accumulator: 4 instead of 5 vector
+// passes per step (x is re-read, r is neither read nor written).  `out` receives
+// the (n, nsig) result; work holds 2*n*nsig elements.  Mathematically equal to
+// cheby_op, rounding differs (tests: within the same 1e-5 of the float64 oracle).
+template <typename T>
+int cheby_clenshaw(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                   const T* vals, double lmax, const double* c, int m, const T* x, int nsig,
+                   T* out, T* work, const gsp_tile_plan* plan, cudaStream_t st) {
+  GSP_REQUIRE(n >= 0 && nsig >= 1, "bad sizes");
+  GSP_REQUIRE(m >= 2, "The coefficients have an invalid shape");
+  GSP_REQUIRE(lmax > 0 && lmax == lmax, "lmax must be positive");
+  if (n == 0) return GSP_OK;
+  const int K = m - 1;
+  const double a2 = 4.0 / lmax;                  // 2 Lt = a2 L - 2 I
+  T* buf[2] = {work, work + n * int64_t(nsig)};
+  double ck = 0, zero = 0;
+  T* xs = const_cast<T*>(x);                     // read-only source block
+  if (K == 1) {                                  // p = c0/2 x + c1 Lt x
+    ck = 0.5 * c[0] - c[1];
+    return cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, x, nullptr, out,
+                                 out, n, nsig, 0, &zero, &zero, c[1] * 2.0 / lmax, ck, 0.0, st);
+  }
+  // b_{K-1} = c_{K-1} x + 2 Lt (c_K x)          (b_K = c_K x is never materialised)
+  int rc = cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, x, nullptr, buf[0],
+                                 buf[0], n, nsig, 0, &zero, &zero, c[K] * a2,
+                                 c[K - 1] - 2.0 * c[K], 0.0, st);
+  if (rc != GSP_OK) return rc;
+  const T* b_cur = buf[0];
+  const T* b_old = nullptr;
+  for (int k = K - 2; k >= 0; --k) {
+    const bool last = k == 0;
+    T* dst = last ? out : (b_old ? const_cast<T*>(b_old) : buf[1]);
+    // middle: b_k = a2 L b_{k+1} - 2 b_{k+1} - b_{k+2} + c_k x ; with b_{k+2} = c_K x for
+    // the first of them.  last: p = (a2/2) L b_1 - b_1 - b_2 + c_0/2 x.
+    const double alpha = last ? 0.5 * a2 : a2, beta = last ? -1.0 : -2.0;
+    double gamma = -1.0;
+    ck = last ? 0.5 * c[0] : c[k];
+    const T* old = b_old;
+    if (!old) {                                   // b_{k+2} = c_K x: fold it into the source term
+      ck -= c[K];
+      gamma = 0.0;
+      old = x;
+    }
+    rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, b_cur, old, dst, xs,
+                               n, nsig, 1, &ck, &zero, alpha, beta, gamma, st, true);
+    if (rc != GSP_OK) return rc;
+    b_old = b_cur;
+    b_cur = dst;
+  }
+  return GSP_OK;
+}
+
 // y = A x for a block of vectors (no recurrence, no r): used by Lanczos and
 // exposed for callers that only need the product (learning.py CG, "next").
 template <typename T>
@@ -329,11 +396,11 @@ int spmm_plain(int64_t n, const int32_t* indptr, const int32_t* indices, const T
 template int cheby_step<float>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
                                const float*, const float*, const float*, float*, float*,
                                int64_t, int, int, const double*, const double*, double,
-                               double, double, cudaStream_t);
+                               double, double, cudaStream_t, bool);
 template int cheby_step<double>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
                                 const double*, const double*, const double*, double*, double*,
                                 int64_t, int, int, const double*, const double*, double,
-                                double, double, cudaStream_t);
+                                double, double, cudaStream_t, bool);
 
 }  // namespace gsp
 
@@ -360,6 +427,14 @@ extern "C" {
                                       indices, data, x_cur, x_old, x_new, r, r_rows, (int)nsig,   \
                                       nscales, ck_host, c0_host, alpha, beta, gamma,              \
                                       gsp::as_stream(stream));                                    \
+  }                                                                                               \
+  int gsp_cheby_clenshaw_##SUF(int64_t n, int64_t nnz, const int32_t* indptr,                     \
+                               const int32_t* indices, const T* data, double lmax,                \
+                               const double* coeffs_host, int m, const T* x, int64_t nsig,        \
+                               T* out, T* work, const gsp_tile_plan* plan_host, void* stream) {   \
+    GSP_REQUIRE(nsig >= 1 && nsig <= (1 << 20), "nsig out of range");                             \
+    return gsp::cheby_clenshaw<T>(n, nnz, indptr, indices, data, lmax, coeffs_host, m, x,         \
+                                  (int)nsig, out, work, plan_host, gsp::as_stream(stream));       \
   }                                                                                               \
   int gsp_spmm_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data,     \
                      const T* x, int64_t nsig, T* y, void* stream) {                              \

@@ -12,12 +12,6 @@
 
 namespace gsp {
 
-template <typename T>
-int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
-               const int32_t* indices, const T* vals, const T* x_cur, const T* x_old,
-               T* x_new, T* r, int64_t r_rows, int nsig, int nscales, const double* ck,
-               const double* c0, double alpha, double beta, double gamma, cudaStream_t st);
-
 constexpr int kVecThreads = 256;
 constexpr int kMaxVecBlocks = 2048;   // partial sums per reduction (scal_dev layout)
 

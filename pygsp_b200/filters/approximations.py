@@ -100,6 +100,29 @@ def cheby_op_device(L, lmax, c, x):
     return r
 
 
+def cheby_clenshaw_device(L, lmax, c, x):
+    """Single filter by Clenshaw's recurrence: x (N, nsig) -> (N, nsig), device to device.
+
+    Same polynomial as :func:`cheby_op_device` with one coefficient row, evaluated
+    backwards (b_k = c_k x + 2 Lt b_{k+1} - b_{k+2}): no accumulator block, 4 instead of
+    5 passes over the signal block per order.  Opt-in: the reference
+    uses the forward recurrence, and so does the default path.
+    """
+    torch = nat.require_cuda()
+    c = np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(-1))
+    if c.size < 2:
+        raise TypeError("The coefficients have an invalid shape")
+    n, nsig = x.shape
+    out = torch.empty((n, nsig), dtype=L.dtype, device=L.device)
+    work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
+    plan = L.tile_plan(nsig, 1)
+    with torch.cuda.device(L.device):
+        nat.call("gsp_cheby_clenshaw_" + nat.suffix(L.dtype), nat.i64(n), nat.i64(L.nnz),
+                 L.indptr, L.indices, L.data, nat.f64(lmax), c, nat.i32(c.size), x,
+                 nat.i64(nsig), out, work, plan, nat.stream_ptr(L.device))
+    return out
+
+
 def cheby_op(G, c, signal, **kwargs):
     r"""Chebyshev polynomial of the graph Laplacian applied to a signal block.
 
@@ -109,6 +132,8 @@ def cheby_op(G, c, signal, **kwargs):
     filter-major row blocks.  ``M < 2`` raises TypeError.  NumPy in -> NumPy
     out, CUDA tensor in -> CUDA tensor out.  The arithmetic type is the
     graph's (float32 by default; the reference always computes in float64).
+    ``clenshaw=True`` (single filter only) evaluates the same polynomial by Clenshaw's
+    backward recurrence, which needs one pass less over the signal block per order.
     """
     if not isinstance(c, np.ndarray):
         c = np.array(c)
@@ -120,7 +145,12 @@ def cheby_op(G, c, signal, **kwargs):
     if x.shape[0] != G.N:
         raise ValueError("First dimension must be the number of vertices "
                          "G.N = {}, got {}.".format(G.N, tuple(x.shape)))
-    r = cheby_op_device(L, G.lmax, c, x)
+    if kwargs.get("clenshaw", False):
+        if c.shape[0] != 1:
+            raise ValueError("clenshaw=True evaluates a single filter")
+        r = cheby_clenshaw_device(L, G.lmax, c[0], x)
+    else:
+        r = cheby_op_device(L, G.lmax, c, x)
     r = r.reshape(c.shape[0] * G.N, x.shape[1])
     if one_d:
         r = r.reshape(-1)

@@ -378,6 +378,23 @@ def test_lmax_brackets_truth(gsp, sensor5k):
     assert lam * (1 - 1e-4) <= G64.lmax / 1.01 <= lam * (1 + 1e-9)
 
 
+@pytest.mark.parametrize("nsig,order", [(64, 30), (64, 1), (64, 2), (64, 3), (32, 17), (5, 12), (128, 8)])
+def test_clenshaw_matches_forward_recurrence(gsp, sensor5k, nsig, order):
+    """Clenshaw evaluation of the same Chebyshev sum."""
+    G, L, _ = sensor5k
+    rng = np.random.default_rng(order * 100 + nsig)
+    x = rng.standard_normal((G.N, nsig))
+    c = orc.cheby_coeff(orc.heat_kernels(G.lmax, 20), G.lmax, order)
+    ref = orc.cheby_op(L, G.lmax, c, x)
+    y = gsp.filters.cheby_op(G, c, x.astype(np.float32), clenshaw=True)
+    assert y.shape == ref.shape and relerr_cols(y, ref) <= F32_TOL
+    G64 = gsp.graphs.Graph(G.W.to_scipy(), dtype=np.float64)
+    G64._lmax, G64._lmax_method = G.lmax, "lanczos"
+    assert relerr_cols(gsp.filters.cheby_op(G64, c, x, clenshaw=True), ref) <= F64_TOL
+    with pytest.raises(ValueError):
+        gsp.filters.cheby_op(G, np.vstack([c, c]), x, clenshaw=True)
+
+
 def test_spmm_dot(gsp, sensor5k):
     G, L, _ = sensor5k
     x = np.random.default_rng(2).standard_normal((G.N, 10))
