@@ -48,9 +48,12 @@ int gsp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
  *   x_new may alias x_old.  Stands for approximations.py:99-103 (first) and
  *   :107-112 (k >= 2).  Used directly by the vertex-partitioned multi-GPU path,
  *   where column indices address a local x_cur that has halo rows appended.
- * gsp_cheby_clenshaw_*: the same single-filter polynomial (m coefficients) evaluated by
- *   Clenshaw's recurrence: K SpMMs, no accumulator (4 vector passes per step instead of 5);
- *   out is (n, nsig), work 2*n*nsig.  Rounding differs from cheby_op, the value does not.
+ * gsp_cheby_clenshaw_*: out = sum_i p_i(L) s_i for nsrc source blocks s_i ((nsrc, n, nsig) in
+ *   memory) and coefficient rows c_i ((nsrc, m) row-major), by ONE backward (Clenshaw)
+ *   recurrence on an (n, nsig) block: K SpMMs in total and no accumulator.  nsrc = 1 is the
+ *   single-filter evaluation; nsrc = Nf is the synthesis of filter.py:313-322 (which runs Nf
+ *   forward recurrences).  out is (n, nsig), work 2*n*nsig.  Same value as the forward
+ *   recurrence, different rounding.
  * gsp_spmm_*: y = L x, scipy `csr_matrix.dot` (approximations.py:99, graph.py:955).
  */
 /* Tiling of the float32 fast path (TMA-staged row tiles, csrc/cheby_tiled.cu).
@@ -116,8 +119,9 @@ int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_
                            const gsp_tile_plan* plan_host, void* stream);                         \
   int gsp_cheby_clenshaw_##SUF(int64_t n, int64_t nnz, const int32_t* indptr,                     \
                                const int32_t* indices, const T* data, double lmax,                \
-                               const double* coeffs_host, int m, const T* x, int64_t nsig,        \
-                               T* out, T* work, const gsp_tile_plan* plan_host, void* stream);    \
+                               const double* coeffs_host, int nsrc, int m, const T* sources,      \
+                               int64_t nsig, T* out, T* work, const gsp_tile_plan* plan_host,     \
+                               void* stream);                                                     \
   int gsp_spmm_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data,     \
                      const T* x, int64_t nsig, T* y, void* stream);
 

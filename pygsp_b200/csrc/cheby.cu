@@ -43,8 +43,8 @@ struct StepCoef {
   T alpha, beta, gamma;
   T half_c0[kMaxScales];   // c[i,0]/2 (first step only)
   T ck[kMaxScales];        // c[i,k]
-  // Clenshaw form (single filter): `r` is a read-only source block s and the step
-  // is x_new += ck[0] * s; nothing is accumulated into r.
+  // Clenshaw form: `r` holds nscales read-only source blocks s_i and the step is
+  // x_new += sum_i ck[i] * s_i; nothing is accumulated into r.
   int add_source;
 };
 
@@ -119,9 +119,12 @@ cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
       xn.v[v] = t;
     }
     if (coef.add_source) {
-      const Vec<T, VEC> sv = load_vec_stream<T, VEC>(r + row * nsig + c0);
+      for (int i = 0; i < nscales; ++i) {
+        const Vec<T, VEC> sv =
+            load_vec_stream<T, VEC>(r + (int64_t(i) * r_rows + row) * nsig + c0);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) xn.v[v] = fma(coef.ck[0], sv.v[v], xn.v[v]);
+        for (int v = 0; v < VEC; ++v) xn.v[v] = fma(coef.ck[i], sv.v[v], xn.v[v]);
+      }
       store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
       continue;
     }
@@ -327,54 +330,91 @@ int cheby_op(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indic
   return GSP_OK;
 }
 
-// Single-filter Chebyshev sum by Clenshaw's recurrence:
-//   b_k = c_k x + 2 Lt b_{k+1} - b_{k+2},  Lt = (2/lmax) L - I,  b_{K+1} = b_{K+2} = 0
-//   p(L) x = c_0/2 x + Lt b_1 - b_2
-// Same K SpMMs as the forward form, but no accumulator: 4 instead of 5 vector
-// passes per step (x is re-read, r is neither read nor written).  `out` receives
-// the (n, nsig) result; work holds 2*n*nsig elements.  Mathematically equal to
-// cheby_op, rounding differs (tests: within the same 1e-5 of the float64 oracle).
+// out = sum_i w[i] * src_i   (src: (nsrc, count) blocks) -- the top Clenshaw term S_K
+template <typename T>
+__global__ void combine_sources(int64_t count, const T* __restrict__ src, int nsrc,
+                                StepCoef<T> coef, T* __restrict__ out) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (; i < count; i += stride) {
+    T acc = T(0);
+    for (int s = 0; s < nsrc; ++s) acc = fma(coef.ck[s], src[int64_t(s) * count + i], acc);
+    out[i] = acc;
+  }
+}
+
+// Chebyshev sums by Clenshaw's recurrence.  For source
+// blocks s_i (nsrc of them, (nsrc, n, nsig) in memory) and coefficient rows c_i:
+//   out = sum_i p_i(L) s_i,   p_i = c_i0/2 + sum_k c_ik T_k(Lt),  Lt = (2/lmax) L - I
+// is evaluated as ONE backward recurrence on an (n, nsig) block,
+//   S_k = sum_i c_ik s_i ;  b_k = S_k + 2 Lt b_{k+1} - b_{k+2} ;  out = S_0/2 + Lt b_1 - b_2,
+// i.e. K SpMMs in total -- the reference's synthesis (filter.py:313-322) runs nsrc
+// separate forward recurrences, nsrc*K SpMMs -- and no accumulator block.  With
+// nsrc = 1 this is the single-filter Clenshaw evaluation (b_K = c_K x is folded into
+// the first step).  work holds 2*n*nsig elements.  Rounding differs from the forward
+// recurrence, the value does not (tests: same tolerance against the float64 oracle).
 template <typename T>
 int cheby_clenshaw(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
-                   const T* vals, double lmax, const double* c, int m, const T* x, int nsig,
-                   T* out, T* work, const gsp_tile_plan* plan, cudaStream_t st) {
-  GSP_REQUIRE(n >= 0 && nsig >= 1, "bad sizes");
+                   const T* vals, double lmax, const double* c, int nsrc, int m, const T* src,
+                   int nsig, T* out, T* work, const gsp_tile_plan* plan, cudaStream_t st) {
+  GSP_REQUIRE(n >= 0 && nsig >= 1 && nsrc >= 1 && nsrc <= kMaxScales, "bad sizes");
   GSP_REQUIRE(m >= 2, "The coefficients have an invalid shape");
   GSP_REQUIRE(lmax > 0 && lmax == lmax, "lmax must be positive");
   if (n == 0) return GSP_OK;
   const int K = m - 1;
   const double a2 = 4.0 / lmax;                  // 2 Lt = a2 L - 2 I
   T* buf[2] = {work, work + n * int64_t(nsig)};
-  double ck = 0, zero = 0;
-  T* xs = const_cast<T*>(x);                     // read-only source block
-  if (K == 1) {                                  // p = c0/2 x + c1 Lt x
-    ck = 0.5 * c[0] - c[1];
-    return cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, x, nullptr, out,
-                                 out, n, nsig, 0, &zero, &zero, c[1] * 2.0 / lmax, ck, 0.0, st);
-  }
-  // b_{K-1} = c_{K-1} x + 2 Lt (c_K x)          (b_K = c_K x is never materialised)
-  int rc = cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, x, nullptr, buf[0],
-                                 buf[0], n, nsig, 0, &zero, &zero, c[K] * a2,
-                                 c[K - 1] - 2.0 * c[K], 0.0, st);
-  if (rc != GSP_OK) return rc;
-  const T* b_cur = buf[0];
+  T* xs = const_cast<T*>(src);                   // read-only source blocks
+  double ck[kMaxScales], zero[kMaxScales];
+  for (int i = 0; i < kMaxScales; ++i) zero[i] = 0;
+  auto coef_col = [&](int k, double scale) {
+    for (int i = 0; i < nsrc; ++i) ck[i] = scale * c[int64_t(i) * m + k];
+  };
+  const T* b_cur;
   const T* b_old = nullptr;
-  for (int k = K - 2; k >= 0; --k) {
+  int k_next;
+  if (nsrc == 1) {
+    if (K == 1) {                                // out = c0/2 x + c1 Lt x
+      return cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, src, nullptr,
+                                   out, out, n, nsig, 0, zero, zero, c[1] * 2.0 / lmax,
+                                   0.5 * c[0] - c[1], 0.0, st);
+    }
+    // b_{K-1} = c_{K-1} x + 2 Lt (c_K x): b_K = c_K x is never materialised
+    int rc = cheby_step_planned<T>(plan, nnz, true, 0, n, indptr, indices, vals, src, nullptr,
+                                   buf[0], buf[0], n, nsig, 0, zero, zero, c[K] * a2,
+                                   c[K - 1] - 2.0 * c[K], 0.0, st);
+    if (rc != GSP_OK) return rc;
+    b_cur = buf[0];
+    k_next = K - 2;
+  } else {
+    // b_K = S_K by one combine pass
+    StepCoef<T> coef;
+    memset(&coef, 0, sizeof(coef));
+    for (int i = 0; i < nsrc; ++i) coef.ck[i] = T(c[int64_t(i) * m + K]);
+    const int64_t count = n * int64_t(nsig);
+    const int blocks = (int)std::min<int64_t>(ceil_div(count, 256), int64_t(sm_count()) * 16);
+    combine_sources<T><<<blocks, 256, 0, st>>>(count, src, nsrc, coef, buf[0]);
+    GSP_LAUNCH_CHECK("combine_sources");
+    b_cur = buf[0];
+    k_next = K - 1;
+  }
+  for (int k = k_next; k >= 0; --k) {
     const bool last = k == 0;
-    T* dst = last ? out : (b_old ? const_cast<T*>(b_old) : buf[1]);
-    // middle: b_k = a2 L b_{k+1} - 2 b_{k+1} - b_{k+2} + c_k x ; with b_{k+2} = c_K x for
-    // the first of them.  last: p = (a2/2) L b_1 - b_1 - b_2 + c_0/2 x.
+    // middle: b_k = a2 L b_{k+1} - 2 b_{k+1} - b_{k+2} + S_k
+    // last  : out = (a2/2) L b_1 - b_1 - b_2 + S_0/2
     const double alpha = last ? 0.5 * a2 : a2, beta = last ? -1.0 : -2.0;
     double gamma = -1.0;
-    ck = last ? 0.5 * c[0] : c[k];
+    coef_col(k, last ? 0.5 : 1.0);
     const T* old = b_old;
-    if (!old) {                                   // b_{k+2} = c_K x: fold it into the source term
-      ck -= c[K];
+    if (!old) {
+      // no b_{k+2} buffer yet: it is c_K x (nsrc == 1, folded into the source term) or 0
+      if (nsrc == 1) ck[0] -= c[K];
       gamma = 0.0;
-      old = x;
+      old = b_cur;                                // any valid block, multiplied by 0
     }
-    rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, b_cur, old, dst, xs,
-                               n, nsig, 1, &ck, &zero, alpha, beta, gamma, st, true);
+    T* dst = last ? out : (b_old ? const_cast<T*>(b_old) : buf[1]);
+    int rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, b_cur, old, dst,
+                                   xs, n, nsig, nsrc, ck, zero, alpha, beta, gamma, st, true);
     if (rc != GSP_OK) return rc;
     b_old = b_cur;
     b_cur = dst;
@@ -430,11 +470,13 @@ extern "C" {
   }                                                                                               \
   int gsp_cheby_clenshaw_##SUF(int64_t n, int64_t nnz, const int32_t* indptr,                     \
                                const int32_t* indices, const T* data, double lmax,                \
-                               const double* coeffs_host, int m, const T* x, int64_t nsig,        \
-                               T* out, T* work, const gsp_tile_plan* plan_host, void* stream) {   \
+                               const double* coeffs_host, int nsrc, int m, const T* sources,      \
+                               int64_t nsig, T* out, T* work, const gsp_tile_plan* plan_host,     \
+                               void* stream) {                                                    \
     GSP_REQUIRE(nsig >= 1 && nsig <= (1 << 20), "nsig out of range");                             \
-    return gsp::cheby_clenshaw<T>(n, nnz, indptr, indices, data, lmax, coeffs_host, m, x,         \
-                                  (int)nsig, out, work, plan_host, gsp::as_stream(stream));       \
+    return gsp::cheby_clenshaw<T>(n, nnz, indptr, indices, data, lmax, coeffs_host, nsrc, m,      \
+                                  sources, (int)nsig, out, work, plan_host,                       \
+                                  gsp::as_stream(stream));                                        \
   }                                                                                               \
   int gsp_spmm_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data,     \
                      const T* x, int64_t nsig, T* y, void* stream) {                              \

@@ -48,7 +48,7 @@ struct TileArgs {
   float half_c0[kTiledMaxScales];
   float ck[kTiledMaxScales];
   gsp_halo_fusion halo;   // all zero when the step does not exchange a halo
-  int add_source;         // Clenshaw form: x_new += ck[0] * (tile of r), r is not written
+  int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
 };
 
 // ----------------------------------------------------------------- PTX helpers
@@ -292,12 +292,19 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
         xn.z = fmaf(gamma, xo.z, xn.z);
         xn.w = fmaf(gamma, xo.w, xn.w);
       }
-      if (NSC == 1 && !FIRST && a.add_source) {
-        const float4 sv = *reinterpret_cast<const float4*>(sm_vec + R * NS + off + c0);
-        xn.x = fmaf(a.ck[0], sv.x, xn.x);
-        xn.y = fmaf(a.ck[0], sv.y, xn.y);
-        xn.z = fmaf(a.ck[0], sv.z, xn.z);
-        xn.w = fmaf(a.ck[0], sv.w, xn.w);
+      if (!FIRST && NSC != 0 && a.add_source) {
+        // Clenshaw form: the r tiles are read-only source blocks, x_new += sum_i ck_i s_i
+#pragma unroll
+        for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
+          if (NSC < 0 && i >= nscales) break;
+          const float4 sv =
+              *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
+          const float w = a.ck[i];
+          xn.x = fmaf(w, sv.x, xn.x);
+          xn.y = fmaf(w, sv.y, xn.y);
+          xn.z = fmaf(w, sv.z, xn.z);
+          xn.w = fmaf(w, sv.w, xn.w);
+        }
       }
       stcs_f4(xn_tile + off, xn);
       if (push_tile) {
@@ -315,7 +322,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
 #pragma unroll
       for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
         if (NSC < 0 && i >= nscales) break;
-        if (NSC == 1 && !FIRST && a.add_source) break;
+        if (!FIRST && a.add_source) break;
         float4 rv;
         const float ck = a.ck[i];
         if (FIRST) {
@@ -471,7 +478,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          int64_t* rows_done, cudaStream_t st, bool add_source) {
   TileArgs a;
   a.add_source = add_source ? 1 : 0;
-  GSP_REQUIRE(!add_source || (nscales == 1 && !first), "add_source needs one source block");
+  GSP_REQUIRE(!add_source || (nscales >= 1 && !first), "add_source needs source blocks");
   memset(&a.halo, 0, sizeof(a.halo));
   if (halo) {
     a.halo = *halo;

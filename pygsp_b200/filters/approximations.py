@@ -100,26 +100,37 @@ def cheby_op_device(L, lmax, c, x):
     return r
 
 
-def cheby_clenshaw_device(L, lmax, c, x):
-    """Single filter by Clenshaw's recurrence: x (N, nsig) -> (N, nsig), device to device.
+def cheby_clenshaw_device(L, lmax, c, sources):
+    """sum_i p_i(L) s_i by ONE backward (Clenshaw) recurrence, device to device.
 
-    Same polynomial as :func:`cheby_op_device` with one coefficient row, evaluated
-    backwards (b_k = c_k x + 2 Lt b_{k+1} - b_{k+2}): no accumulator block, 4 instead of
-    5 passes over the signal block per order.  Opt-in: the reference
-    uses the forward recurrence, and so does the default path.
+    ``sources``: (nsrc, N, nsig) tensor (or (N, nsig) for a single filter), ``c``:
+    (nsrc, M) coefficients.  With one source this is the single-filter filtering of
+    :func:`cheby_op_device` at 4 instead of 5 passes over the signal block per order; with
+    nsrc = Nf sources it is the *synthesis* of ``Filter.filter`` in K SpMMs instead of the
+    reference's Nf * K (filter.py:313-322), because Clenshaw's recurrence is linear in its
+    source term: b_k = sum_i c_ik s_i + 2 Lt b_{k+1} - b_{k+2}  (SURVEY.md 8f).
+    Returns (N, nsig).
     """
     torch = nat.require_cuda()
-    c = np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(-1))
-    if c.size < 2:
+    c = np.ascontiguousarray(np.atleast_2d(np.asarray(c, dtype=np.float64)))
+    if c.shape[1] < 2:
         raise TypeError("The coefficients have an invalid shape")
-    n, nsig = x.shape
+    if sources.dim() == 2:
+        sources = sources[None]
+    nsrc, n, nsig = sources.shape
+    if nsrc != c.shape[0]:
+        raise ValueError("one coefficient row per source block")
+    if nsrc > 16:
+        raise ValueError("at most 16 source blocks per call")
+    sources = sources.contiguous()
     out = torch.empty((n, nsig), dtype=L.dtype, device=L.device)
     work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
-    plan = L.tile_plan(nsig, 1)
+    plan = L.tile_plan(nsig, nsrc)
     with torch.cuda.device(L.device):
         nat.call("gsp_cheby_clenshaw_" + nat.suffix(L.dtype), nat.i64(n), nat.i64(L.nnz),
-                 L.indptr, L.indices, L.data, nat.f64(lmax), c, nat.i32(c.size), x,
-                 nat.i64(nsig), out, work, plan, nat.stream_ptr(L.device))
+                 L.indptr, L.indices, L.data, nat.f64(lmax), c, nat.i32(nsrc),
+                 nat.i32(c.shape[1]), sources, nat.i64(nsig), out, work, plan,
+                 nat.stream_ptr(L.device))
     return out
 
 

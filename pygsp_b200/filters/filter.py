@@ -36,6 +36,10 @@ class Filter:
         self.shape = (self.n_features_out, self.n_features_in)
         self.n_filters = self.n_features_in * self.n_features_out
         self.Nf = self.n_filters
+        # synthesis as ONE backward recurrence (K SpMMs) instead of the reference's Nf
+        # forward recurrences (Nf * K SpMMs); same value, different rounding.  Set to
+        # False to reproduce the reference's operation order.
+        self.fused_synthesis = True
 
     def _get_extra_repr(self):
         return dict()
@@ -119,10 +123,13 @@ class Filter:
         else:                                                    # synthesis
             x, _, kind = approximations._as_device_block(view, s.reshape(N, -1))
             x = x.reshape(N, n_signals, n_features_in)
-            out = torch.zeros((N, n_signals), dtype=L.dtype, device=L.device)
-            for i in range(n_features_in):
-                xi = x[:, :, i].contiguous()
-                out += approximations.cheby_op_device(L, self.G.lmax, c[i], xi)[0]
+            if self.fused_synthesis and n_features_in <= 16:
+                out = approximations.cheby_clenshaw_device(L, self.G.lmax, c, x.permute(2, 0, 1))
+            else:
+                out = torch.zeros((N, n_signals), dtype=L.dtype, device=L.device)
+                for i in range(n_features_in):
+                    xi = x[:, :, i].contiguous()
+                    out += approximations.cheby_op_device(L, self.G.lmax, c[i], xi)[0]
             out = out[:, :, None]
         out = out.squeeze()
         return approximations._leave_device(out, kind)

@@ -395,6 +395,71 @@ def test_clenshaw_matches_forward_recurrence(gsp, sensor5k, nsig, order):
         gsp.filters.cheby_op(G, np.vstack([c, c]), x, clenshaw=True)
 
 
+def test_heavy_rows_fall_back_to_rowgroup(gsp):
+    """A hub whose CSR slab cannot fit a shared-memory stage: the tile plan declines and
+    the row-group kernel serves the whole matrix (same results, float32 Nsig=64)."""
+    from scipy import sparse
+    n = 70000
+    rng = np.random.default_rng(4)
+    hub = np.zeros(n - 1, dtype=np.int64)
+    ring = np.arange(1, n)
+    rows = np.concatenate([hub, ring[:-1]])
+    cols = np.concatenate([ring, ring[1:]])
+    w = rng.uniform(0.5, 1.5, rows.size)
+    A = sparse.coo_matrix((w, (rows, cols)), shape=(n, n)).tocsr()
+    A = A + A.T
+    G = gsp.graphs.Graph(A)
+    assert G.L.tile_plan(64, 1) is None                   # 70 000-entry row: no tiling
+    G.estimate_lmax(method="bounds")
+    L = orc.laplacian(A)
+    x = rng.standard_normal((n, 64))
+    c = orc.cheby_coeff(orc.heat_kernels(G.lmax, 30), G.lmax, 10)
+    assert relerr_cols(gsp.filters.cheby_op(G, c, x), orc.cheby_op(L, G.lmax, c, x)) <= F32_TOL
+
+
+def test_normalized_and_directed_graphs_filter(gsp, golden):
+    """lap_type='normalized' and a directed adjacency go through the same filter path."""
+    from scipy import sparse
+    rng = np.random.default_rng(8)
+    A = sparse.random(3000, 3000, 0.002, random_state=8, format="csr")       # directed
+    A.setdiag(0); A.eliminate_zeros()
+    x = rng.standard_normal((3000, 32))
+    for lap in ("combinatorial", "normalized"):
+        G = gsp.graphs.Graph(A, lap_type=lap)
+        assert G.is_directed()
+        L = orc.laplacian(A, lap)
+        Ld = G.L.to_scipy()
+        np.testing.assert_array_equal(Ld.indptr, L.indptr)
+        np.testing.assert_array_equal(Ld.indices, L.indices)
+        np.testing.assert_allclose(Ld.data, L.data, rtol=3e-6, atol=1e-7)
+        G.estimate_lmax()
+        c = orc.cheby_coeff(orc.mexican_hat_kernels(G.lmax, Nf=3), G.lmax, 20)
+        # the oracle takes the device's float32 Laplacian values so that only the
+        # recurrence is compared
+        ref = orc.cheby_op(Ld.astype(np.float64), G.lmax, c, x)
+        assert relerr_cols(gsp.filters.cheby_op(G, c, x), ref) <= F32_TOL
+
+
+@pytest.mark.parametrize("nf,nsig,order", [(5, 64, 30), (2, 32, 12), (6, 3, 20), (3, 64, 1), (16, 8, 9)])
+def test_fused_synthesis_matches_reference_order(gsp, sensor5k, nf, nsig, order):
+    """synthesis as one backward recurrence == sum of forward ones."""
+    G, L, _ = sensor5k
+    rng = np.random.default_rng(nf * 1000 + nsig)
+    s = rng.standard_normal((G.N, nsig, nf))
+    bank = gsp.filters.Heat(G, scale=[3.0 * (i + 1) for i in range(nf)])
+    ref = orc.filter_signal(L, G.lmax, orc.heat_kernels(G.lmax, bank.scale), s, order=order)
+    assert bank.fused_synthesis
+    y = bank.filter(s.astype(np.float32), order=order)
+    assert y.shape == ref.shape and relerr_cols(y, ref) <= F32_TOL
+    bank.fused_synthesis = False                        # the reference's operation order
+    y2 = bank.filter(s.astype(np.float32), order=order)
+    assert relerr_cols(y2, ref) <= F32_TOL
+    G64 = gsp.graphs.Graph(G.W.to_scipy(), dtype=np.float64)
+    G64._lmax, G64._lmax_method = G.lmax, "lanczos"
+    b64 = gsp.filters.Heat(G64, scale=bank.scale)
+    assert relerr_cols(b64.filter(s, order=order), ref) <= F64_TOL
+
+
 def test_spmm_dot(gsp, sensor5k):
     G, L, _ = sensor5k
     x = np.random.default_rng(2).standard_normal((G.N, 10))
