@@ -48,6 +48,7 @@ struct TileArgs {
   float half_c0[kTiledMaxScales];
   float ck[kTiledMaxScales];
   gsp_halo_fusion halo;   // all zero when the step does not exchange a halo
+  int l2_hint;            // evict-first hint on the streamed TMA copies
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
 };
 
@@ -87,6 +88,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
           "r"(smem_addr(dst)),
       "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_addr(bar))
       : "memory");
+}
+
+// same, with an L2 eviction-priority hint (streamed operands: read once per step)
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes,
+                                              uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst)),
+      "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
@@ -151,6 +167,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   if (warp == 0) {
     // ------------------------------------------------------------- producer
     if (lane != 0) return;
+    // x_old / r / CSR are touched once per step: mark them evict-first so that the
+    // L2 keeps the x_cur lines the gathers re-use (GSPB200_TILE_HINT=0 disables)
+    const bool hint = a.l2_hint != 0;
+    const uint64_t pol = l2_policy_evict_first();
     int it = 0;
     // the tile's first / last CSR offsets are fetched one tile ahead, so that their
     // DRAM latency is not in series with the wait for a free slot
@@ -192,15 +212,28 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const uint32_t bytes = uint32_t(R) * 4u + 2u * slab + (FIRST ? 0u : tile_vec * (1 + a.nscales));
       mbar_expect_tx(full + s, bytes);
       bulk_g2s(sm_ptr, a.indptr + r0, uint32_t(R) * 4u, full + s);
-      if (slab) {
-        bulk_g2s(sm_col, a.indices + a0, slab, full + s);
-        bulk_g2s(sm_val, a.vals + a0, slab, full + s);
-      }
-      if (!FIRST) {
-        bulk_g2s(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s);
-        for (int i = 0; i < a.nscales; ++i)
-          bulk_g2s(sm_vec + size_t(i + 1) * R * nsig,
-                   a.r + (int64_t(i) * a.r_rows + r0) * nsig, tile_vec, full + s);
+      if (hint) {
+        if (slab) {
+          bulk_g2s_hint(sm_col, a.indices + a0, slab, full + s, pol);
+          bulk_g2s_hint(sm_val, a.vals + a0, slab, full + s, pol);
+        }
+        if (!FIRST) {
+          bulk_g2s_hint(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s, pol);
+          for (int i = 0; i < a.nscales; ++i)
+            bulk_g2s_hint(sm_vec + size_t(i + 1) * R * nsig,
+                          a.r + (int64_t(i) * a.r_rows + r0) * nsig, tile_vec, full + s, pol);
+        }
+      } else {
+        if (slab) {
+          bulk_g2s(sm_col, a.indices + a0, slab, full + s);
+          bulk_g2s(sm_val, a.vals + a0, slab, full + s);
+        }
+        if (!FIRST) {
+          bulk_g2s(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s);
+          for (int i = 0; i < a.nscales; ++i)
+            bulk_g2s(sm_vec + size_t(i + 1) * R * nsig,
+                     a.r + (int64_t(i) * a.r_rows + r0) * nsig, tile_vec, full + s);
+        }
       }
     }
     return;
@@ -478,6 +511,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          int64_t* rows_done, cudaStream_t st, bool add_source) {
   TileArgs a;
   a.add_source = add_source ? 1 : 0;
+  a.l2_hint = env_int("GSPB200_TILE_HINT", 1);
   GSP_REQUIRE(!add_source || (nscales >= 1 && !first), "add_source needs source blocks");
   memset(&a.halo, 0, sizeof(a.halo));
   if (halo) {
