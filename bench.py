@@ -312,20 +312,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    # the clock sampler (nvidia-smi takes a while to start) runs from before the warm-up
+    # to the end of the timed region: every sample is taken under this workload
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        run_dev(x)
-    barrier()
-    launches0 = lib.gsp_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for _ in range(warm + 100):                      # same count on every rank (~1 s of load)
+            run_dev(x)
         barrier()
+        launches0 = lib.gsp_launch_count()
         start.record()
         for _ in range(args.steps):
             run_dev(x)
         stop.record()
         barrier()
-    launches = int(lib.gsp_launch_count() - launches0)
+        launches = int(lib.gsp_launch_count() - launches0)
+        time.sleep(0.25)                                 # let the sampler emit its last line
     t_all = torch.tensor([start.elapsed_time(stop) / 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)

@@ -185,6 +185,30 @@ int gsp_halo_push_f64(int64_t n_send, const int64_t* src_row, const int32_t* dst
 int gsp_halo_wait(const uint64_t* flags, const int32_t* neighbor_ids, int n_neighbors,
                   uint64_t value, void* stream);
 
+/* ------------------------------------------------------ on-device graph construction ---
+ * gsp_grid2d_*: adjacency of pygsp/graphs/grid2d.py:40-89 (n1 x n2 grid, 4 neighbours, unit
+ *     weights, row-major numbering) as canonical CSR; count writes indptr (n1*n2 + 1).
+ * gsp_knn_grid: k nearest neighbours (self excluded) of n points in 2-D / 3-D by a
+ *     uniform cell grid -- the scipy.spatial.KDTree query of nngraph.py:213-216.
+ *     points (n, dim) double; lo/hi: bounding box, cells: grid resolution (host arrays
+ *     of length dim); outputs (n, k) row-major, ascending distance, ties by index.
+ * gsp_knn_to_csr_*: directed k-NN matrix W[i, nn] = exp(-d^2/sigma) as CSR with sorted
+ *     rows (nngraph.py:221-226,289); symmetrise with gsp_csr_transpose / _average.
+ */
+int gsp_grid2d_count(int64_t n1, int64_t n2, int32_t* indptr, void* stream);
+int gsp_grid2d_fill_f32(int64_t n1, int64_t n2, const int32_t* indptr, int32_t* indices,
+                        float* data, void* stream);
+int gsp_grid2d_fill_f64(int64_t n1, int64_t n2, const int32_t* indptr, int32_t* indices,
+                        double* data, void* stream);
+int gsp_knn_grid(int64_t n, int dim, const double* points, int k, const double* lo_host,
+                 const double* hi_host, const int32_t* cells_host, int32_t* nn_idx,
+                 double* nn_dist, void* stream);
+int gsp_knn_to_csr_f32(int64_t n, int k, const int32_t* nn_idx, const double* nn_dist,
+                       double sigma, int32_t* indptr, int32_t* indices, float* data, void* stream);
+int gsp_knn_to_csr_f64(int64_t n, int k, const int32_t* nn_idx, const double* nn_dist,
+                       double sigma, int32_t* indptr, int32_t* indices, double* data,
+                       void* stream);
+
 #define GSPB200_DECLARE_GRAPH_API(SUF, T)                                                        \
   int gsp_csr_inspect_##SUF(int64_t n, const int32_t* indptr, const int32_t* indices,            \
                             const T* data, int64_t* stats_dev, void* stream);                    \

@@ -2,4 +2,5 @@
 from .csr import DeviceCSR  # noqa: F401
 from .graph import Graph  # noqa: F401
 from .generators import (Grid2d, Logo, NNGraph, Ring, Sensor, SensorStrips,  # noqa: F401
-                         StochasticBlockModel, laplacian_rows, morton_order, sbm_adjacency)
+                         StochasticBlockModel, grid2d_adjacency_device, knn_adjacency_device,
+                         knn_device, laplacian_rows, morton_order, sbm_adjacency)

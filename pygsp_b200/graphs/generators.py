@@ -11,8 +11,10 @@ import os
 import numpy as np
 from scipy import sparse, spatial
 
+from .. import _native as nat
 from .. import utils
-from .graph import Graph
+from .csr import DeviceCSR
+from .graph import Graph, _torch_dtype, symmetrize_average_device
 
 _DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
 
@@ -82,19 +84,88 @@ class Grid2d(Graph):
     Same graph and row-major vertex numbering as pygsp/graphs/grid2d.py:40-89.
     """
 
-    def __init__(self, N1=16, N2=None, **kwargs):
+    def __init__(self, N1=16, N2=None, backend="device", **kwargs):
         if N2 is None:
             N2 = N1
         self.N1, self.N2 = N1, N2
         N = N1 * N2
-        right = np.ones(N - 1)
-        right[N2 - 1::N2] = 0                       # no edge across a row end
-        W = sparse.diags([right, np.ones(N - N2)], [1, N2], shape=(N, N), format="csr")
-        W.eliminate_zeros()
-        W = (W + W.T).tocsr()
+        if backend == "device":                     # stencil written straight into HBM
+            W = grid2d_adjacency_device(N1, N2, kwargs.get("dtype"), kwargs.get("device"))
+        else:
+            right = np.ones(N - 1)
+            right[N2 - 1::N2] = 0                   # no edge across a row end
+            W = sparse.diags([right, np.ones(N - N2)], [1, N2], shape=(N, N), format="csr")
+            W.eliminate_zeros()
+            W = (W + W.T).tocsr()
         x = np.tile(np.arange(N2) / float(N2), N1)
         y = np.repeat(np.arange(N1)[::-1] / float(N1), N2)
         super().__init__(W, coords=np.stack([x, y], axis=1), **kwargs)
+
+
+def _device_of(device):
+    torch = nat.require_cuda()
+    return torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+
+
+def grid2d_adjacency_device(N1, N2, dtype=None, device=None):
+    """Grid2d adjacency built by ``gsp_grid2d_*`` (no host matrix)."""
+    torch = nat.require_cuda()
+    dev, dt = _device_of(device), _torch_dtype(torch, dtype)
+    n = N1 * N2
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.call("gsp_grid2d_count", nat.i64(N1), nat.i64(N2), indptr, nat.stream_ptr(dev))
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz, dtype=dt, device=dev)
+        nat.call("gsp_grid2d_fill_" + nat.suffix(dt), nat.i64(N1), nat.i64(N2), indptr, indices,
+                 data, nat.stream_ptr(dev))
+    return DeviceCSR(indptr, indices, data, (n, n))
+
+
+def knn_device(points, k, device=None, points_per_cell=3.0):
+    """k nearest neighbours of every point (self excluded) on the GPU.
+
+    Stands in for ``scipy.spatial.KDTree(X).query(X, k + 1)`` (nngraph.py:213-216):
+    returns (nn, dist), both (N, k) CUDA tensors, ascending distance.  2-D / 3-D, k <= 32.
+    """
+    torch = nat.require_cuda()
+    dev = _device_of(device)
+    pts = torch.as_tensor(np.asarray(points, dtype=np.float64) if not torch.is_tensor(points)
+                          else points).to(device=dev, dtype=torch.float64).contiguous()
+    n, dim = pts.shape
+    lo = pts.min(dim=0).values.cpu().numpy().astype(np.float64)
+    hi = pts.max(dim=0).values.cpu().numpy().astype(np.float64)
+    span = np.maximum(hi - lo, 1e-300)
+    # cubic cells holding ~points_per_cell points on average
+    h = (np.prod(span) * points_per_cell / n) ** (1.0 / dim)
+    cells = np.maximum(np.floor(span / h), 1).astype(np.int32)
+    while np.prod(cells.astype(np.int64)) >= 2 ** 31:
+        cells = np.maximum(cells // 2, 1)
+    nn = torch.empty((n, k), dtype=torch.int32, device=dev)
+    dist = torch.empty((n, k), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nat.call("gsp_knn_grid", nat.i64(n), nat.i32(dim), pts, nat.i32(k),
+                 np.ascontiguousarray(lo), np.ascontiguousarray(hi), np.ascontiguousarray(cells),
+                 nn, dist, nat.stream_ptr(dev))
+    return nn, dist
+
+
+def knn_adjacency_device(points, k, sigma=None, dtype=None, device=None):
+    """Symmetric Gaussian k-NN adjacency (nngraph.py:213-226,289-297) built on the GPU."""
+    torch = nat.require_cuda()
+    dev, dt = _device_of(device), _torch_dtype(torch, dtype)
+    nn, dist = knn_device(points, k, dev)
+    n = nn.shape[0]
+    if sigma is None:
+        sigma = float(dist.mean().item())
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(n * k, dtype=torch.int32, device=dev)
+    data = torch.empty(n * k, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        nat.call("gsp_knn_to_csr_" + nat.suffix(dt), nat.i64(n), nat.i32(k), nn, dist,
+                 nat.f64(sigma), indptr, indices, data, nat.stream_ptr(dev))
+    return symmetrize_average_device(DeviceCSR(indptr, indices, data, (n, n))), sigma
 
 
 class NNGraph(Graph):
@@ -106,7 +177,8 @@ class NNGraph(Graph):
     ``center`` / ``rescale`` preprocessing (:127-136).
     """
 
-    def __init__(self, Xin, k=10, sigma=None, center=True, rescale=True, order=None, **kwargs):
+    def __init__(self, Xin, k=10, sigma=None, center=True, rescale=True, order=None,
+                 backend="host", **kwargs):
         Xin = np.asarray(Xin, dtype=np.float64)
         N, d = Xin.shape
         if k >= N:
@@ -120,14 +192,18 @@ class NNGraph(Graph):
             X = X[morton_order(X)]
         elif order is not None:
             X = X[np.asarray(order)]
-        D, NN = spatial.cKDTree(X).query(X, k=k + 1, workers=-1)
-        if sigma is None:
-            sigma = np.mean(D[:, 1:])
-        self.k, self.sigma = k, sigma
-        rows = np.repeat(np.arange(N), k)
-        W = sparse.csr_matrix((np.exp(-D[:, 1:].ravel() ** 2 / float(sigma)),
-                               (rows, NN[:, 1:].ravel())), shape=(N, N))
-        W = utils.symmetrize(W, "average").tocsr()
+        if backend == "device":                     # grid-hash k-NN + symmetrisation in HBM
+            W, sigma = knn_adjacency_device(X, k, sigma, kwargs.get("dtype"), kwargs.get("device"))
+            self.k, self.sigma = k, sigma
+        else:
+            D, NN = spatial.cKDTree(X).query(X, k=k + 1, workers=-1)
+            if sigma is None:
+                sigma = np.mean(D[:, 1:])
+            self.k, self.sigma = k, sigma
+            rows = np.repeat(np.arange(N), k)
+            W = sparse.csr_matrix((np.exp(-D[:, 1:].ravel() ** 2 / float(sigma)),
+                                   (rows, NN[:, 1:].ravel())), shape=(N, N))
+            W = utils.symmetrize(W, "average").tocsr()
         super().__init__(W, coords=X, **kwargs)
 
 
@@ -140,8 +216,9 @@ class Sensor(NNGraph):
     along a Z-curve (an isomorphic graph with gather-friendly numbering).
     """
 
-    def __init__(self, N=64, k=6, seed=None, order=None, **kwargs):
+    def __init__(self, N=64, k=6, seed=None, order=None, backend="host", **kwargs):
         self.seed = seed
+        kwargs["backend"] = backend
         coords = np.random.default_rng(seed).uniform(0, 1, (N, 2))
         kwargs.setdefault("plotting", {"limits": np.array([0, 1, 0, 1])})
         super().__init__(coords, k=k, center=False, rescale=False, order=order, **kwargs)

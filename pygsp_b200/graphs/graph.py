@@ -392,6 +392,27 @@ class Graph:
             "filtering path this engine implements; use estimate_lmax().")
 
 
+def symmetrize_average_device(W):
+    """(W + W^T)/2 of a DeviceCSR, on the device (utils.py:247-248)."""
+    torch = nat.require_cuda()
+    n, dev, sfx = W.shape[0], W.device, nat.suffix(W.dtype)
+
+    def call(name, *args):
+        with torch.cuda.device(dev):
+            nat.call(name + "_" + sfx, *args, nat.stream_ptr(dev))
+    tp = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    ti = torch.empty(W.nnz, dtype=torch.int32, device=dev)
+    td = torch.empty(W.nnz, dtype=W.dtype, device=dev)
+    call("gsp_csr_transpose", nat.i64(n), nat.i64(W.nnz), W.indptr, W.indices, W.data, tp, ti, td)
+    sp = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    call("gsp_csr_average_count", nat.i64(n), W.indptr, W.indices, W.data, tp, ti, td, sp)
+    nnz = int(sp[-1].item()) if n else 0
+    si = torch.empty(nnz, dtype=torch.int32, device=dev)
+    sd = torch.empty(nnz, dtype=W.dtype, device=dev)
+    call("gsp_csr_average_fill", nat.i64(n), W.indptr, W.indices, W.data, tp, ti, td, sp, si, sd)
+    return DeviceCSR(sp, si, sd, W.shape)
+
+
 def _torch_dtype(torch, dtype):
     if dtype is None:
         return torch.float32

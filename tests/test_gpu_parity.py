@@ -460,6 +460,55 @@ def test_fused_synthesis_matches_reference_order(gsp, sensor5k, nf, nsig, order)
     assert relerr_cols(b64.filter(s, order=order), ref) <= F64_TOL
 
 
+@pytest.mark.parametrize("n,dim,k", [(20000, 2, 10), (6000, 3, 16), (500, 2, 32), (40, 2, 3)])
+def test_device_knn_equals_kdtree(gsp, n, dim, k):
+    """grid-hash k-NN on the GPU vs scipy.spatial.cKDTree (nngraph.py:213-216)."""
+    from scipy import spatial
+    pts = np.random.default_rng(n + dim).uniform(size=(n, dim))
+    if n == 500:
+        pts[:, 0] *= 7.0                                   # anisotropic box
+    D, NN = spatial.cKDTree(pts).query(pts, k=k + 1)
+    nn, dist = gsp.graphs.knn_device(pts, k)
+    np.testing.assert_array_equal(nn.cpu().numpy(), NN[:, 1:])
+    np.testing.assert_allclose(dist.cpu().numpy(), D[:, 1:], rtol=1e-12, atol=1e-15)
+
+
+def test_device_generators_equal_host_generators(gsp):
+    """Sensor / NNGraph / Grid2d built in HBM give the same adjacency as the host builders."""
+    for kw in (dict(N=30000, k=10, seed=3, order="morton"), dict(N=2000, k=6, seed=1)):
+        H = gsp.graphs.Sensor(backend="host", dtype=np.float64, **kw)
+        D = gsp.graphs.Sensor(backend="device", dtype=np.float64, **kw)
+        Wh, Wd = H.W.to_scipy(), D.W.to_scipy()
+        np.testing.assert_array_equal(Wd.indptr, Wh.indptr)
+        np.testing.assert_array_equal(Wd.indices, Wh.indices)
+        np.testing.assert_allclose(Wd.data, Wh.data, rtol=1e-12)
+        assert abs(D.sigma - H.sigma) <= 1e-13 * H.sigma and D.n_edges == H.n_edges
+        np.testing.assert_array_equal(D.L.to_scipy().indices, H.L.to_scipy().indices)
+    pts = np.random.default_rng(0).normal(size=(5000, 3))
+    H = gsp.graphs.NNGraph(pts, k=8, backend="host", dtype=np.float64)
+    D = gsp.graphs.NNGraph(pts, k=8, backend="device", dtype=np.float64)
+    np.testing.assert_array_equal(D.W.to_scipy().indices, H.W.to_scipy().indices)
+    np.testing.assert_allclose(D.W.to_scipy().data, H.W.to_scipy().data, rtol=1e-11)
+    for shape in ((7, 5), (1, 9), (64, 64)):
+        H = gsp.graphs.Grid2d(*shape, backend="host")
+        D = gsp.graphs.Grid2d(*shape, backend="device")
+        np.testing.assert_array_equal(D.W.to_scipy().indptr, H.W.to_scipy().indptr)
+        np.testing.assert_array_equal(D.W.to_scipy().indices, H.W.to_scipy().indices)
+        np.testing.assert_array_equal(D.W.to_scipy().data, H.W.to_scipy().data)
+        assert D.n_edges == H.n_edges
+
+
+def test_arbitrary_kernel_high_order(gsp, sensor5k):
+    """Any kernel function plugs into Filter: the Green kernel 1/(eps + x) at order 100 is
+    what reduction.interpolate feeds to the same path (reduction.py:150-193)."""
+    G, L, _ = sensor5k
+    green = lambda x: 1.0 / (0.05 + x)
+    x = np.random.default_rng(3).standard_normal((G.N, 16))
+    y = gsp.filters.Filter(G, green).filter(x.astype(np.float32), order=100)
+    ref = orc.filter_signal(L, G.lmax, [green], x, order=100)
+    assert relerr_cols(y, ref) <= F32_TOL
+
+
 def test_spmm_dot(gsp, sensor5k):
     G, L, _ = sensor5k
     x = np.random.default_rng(2).standard_normal((G.N, 10))
