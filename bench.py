@@ -73,8 +73,10 @@ def algorithmic_bytes(n, nnz, nsig, nscales, order, itemsize=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms by one long-running
+    process (started early: nvidia-smi needs ~1 s to come up); ``summary(t0, t1)`` keeps
+    the samples whose timestamp falls inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -85,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -94,33 +96,50 @@ class ClockSampler:
         return self
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            cells = [c.strip() for c in line.split(",")]
+            stamp = time.time()                          # arrival time (pipes may batch lines) ...
+            try:                                         # ... so prefer nvidia-smi's own timestamp
+                stamp = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except (ValueError, IndexError):
+                pass
+            self.rows.append((stamp, cells))
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
-        sm, mx, reasons = [], [], set()
+    def summary(self, t0=None, t1=None):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(rows):
+            sm, mx, power, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                except (ValueError, IndexError):
+                    continue
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, power, reasons
+        window = "timed region"
+        rows = [x for x in self.rows if t0 is None or (t0 - 0.02 <= x[0] <= t1 + 0.03)]
+        sm, mx, power, reasons = collect(rows)
+        if not sm:                                   # region shorter than a sampling period
+            window = "warm-up + timed region"
+            rows = [x for x in self.rows if t0 is None or x[0] >= t0 - 1.0]
+            sm, mx, power, reasons = collect(rows)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": float(max(power)), "reasons": sorted(reasons),
+                "samples": len(sm), "window": window}
 
 
 def measured_peak():
@@ -278,6 +297,9 @@ def run_ours(args):
     lib = gsp._native.lib()
     lib.gsp_launch_count.restype = ctypes.c_uint64
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()                       # running long before the timed region
+
     # ---- build the workload (untimed)
     if world == 1:
         G = build_single(gsp, wl, rank)
@@ -312,22 +334,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    # the clock sampler (nvidia-smi takes a while to start) runs from before the warm-up
-    # to the end of the timed region: every sample is taken under this workload
     warm = max(args.warmup, 3)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        for _ in range(warm + 100):                      # same count on every rank (~1 s of load)
-            run_dev(x)
-        barrier()
-        launches0 = lib.gsp_launch_count()
-        start.record()
-        for _ in range(args.steps):
-            run_dev(x)
-        stop.record()
-        barrier()
-        launches = int(lib.gsp_launch_count() - launches0)
-        time.sleep(0.25)                                 # let the sampler emit its last line
+    for _ in range(warm):
+        run_dev(x)
+    barrier()
+    launches0 = lib.gsp_launch_count()
+    t_region0 = time.time()
+    start.record()
+    for _ in range(args.steps):
+        run_dev(x)
+    stop.record()
+    barrier()
+    t_region1 = time.time()
+    launches = int(lib.gsp_launch_count() - launches0)
+    time.sleep(0.1)                                      # let the sampler emit its last lines
+    clocks.__exit__()
     t_all = torch.tensor([start.elapsed_time(stop) / 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -409,7 +431,7 @@ def run_ours(args):
                    "api": "Heat(G, 50).filter(pinned_host_tensor, order=30)" if world == 1 else
                           "PartitionedCheby.cheby_op(pinned host block -> H2D -> op -> D2H)"},
            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "halo": halo,
-           "clocks": clocks.summary()}
+           "clocks": clocks.summary(t_region0, t_region1)}
     print(json.dumps(out))
     if world > 1:
         dist.barrier()
