@@ -33,7 +33,19 @@ sys.path.insert(0, ROOT)
 METRIC = "cheby_op_filtered_vertices_per_sec"
 UNIT = "vertex*signal*order/s"
 WORKLOAD = dict(name="sensor_knn2d_N1e6_k10_seed0_morton_heat50_order30_nsig64",
-                N=1_000_000, k=10, seed=0, nsig=64, order=30, scale=50.0)
+                N=1_000_000, k=10, seed=0, nsig=64, order=30, scale=50.0, graph="sensor",
+                bank="heat", nscales=1)
+# the other BASELINE configurations, single GPU, for the record (profiles/): --workload NAME
+WORKLOADS = {
+    "config2": WORKLOAD,
+    "knn10m": dict(WORKLOAD, name="sensor_knn2d_N1e7_k10_seed0_morton_heat50_order30_nsig64",
+                   N=10_000_000),
+    "config3": dict(name="grid2d_3162x3162_mexicanhat6_order50_nsig64", N=3162 * 3162, k=4,
+                    seed=0, nsig=64, order=50, scale=50.0, graph="grid2d", bank="mexicanhat",
+                    nscales=6),
+    "config4": dict(name="sbm_N1e7_k8_p5e-6_q5e-7_heat50_order30_nsig32", N=10_000_000, k=8,
+                    seed=0, nsig=32, order=30, scale=50.0, graph="sbm", bank="heat", nscales=1),
+}
 
 
 def parse():
@@ -43,6 +55,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override vertex count (debug)")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="single-GPU record runs of the other BASELINE configs")
     ap.add_argument("--cpu-columns", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -250,8 +264,13 @@ def run_reference(args):
 # ------------------------------------------------------------------- our arm
 def build_single(gsp, wl, rank):
     """N = 1: Graph API end to end (device Laplacian, device Lanczos lmax)."""
-    W = host_graph(wl["N"], wl["k"], wl["seed"])
-    G = gsp.graphs.Graph(W)
+    if wl["graph"] == "grid2d":
+        side = int(round(wl["N"] ** 0.5))
+        G = gsp.graphs.Grid2d(side, side)             # stencil written on the device
+    elif wl["graph"] == "sbm":
+        G = gsp.graphs.StochasticBlockModel(wl["N"], k=wl["k"], p=5e-6, q=5e-7, seed=wl["seed"])
+    else:
+        G = gsp.graphs.Graph(host_graph(wl["N"], wl["k"], wl["seed"]))
     G.estimate_lmax()
     return G
 
@@ -290,10 +309,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    wl = dict(WORKLOAD)
+    wl = dict(WORKLOADS[args.workload])
     if args.n:
         wl["N"] = args.n
     n, nsig, order = wl["N"], wl["nsig"], wl["order"]
+    if world > 1 and args.workload != "config2":
+        raise SystemExit("--workload is a single-GPU option")
     lib = gsp._native.lib()
     lib.gsp_launch_count.restype = ctypes.c_uint64
 
@@ -303,8 +324,10 @@ def run_ours(args):
     # ---- build the workload (untimed)
     if world == 1:
         G = build_single(gsp, wl, rank)
+        n = wl["N"] = G.N
         L, lmax, nnz = G.L, G.lmax, G.L.nnz
-        heat = gsp.filters.Heat(G, scale=wl["scale"])
+        heat = (gsp.filters.MexicanHat(G, Nf=wl["nscales"]) if wl["bank"] == "mexicanhat"
+                else gsp.filters.Heat(G, scale=wl["scale"]))
         c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
         run_dev = lambda xx: apx.cheby_op_device(L, lmax, c, xx)
         run_host = lambda xh: heat.filter(xh, order=order)
@@ -357,21 +380,23 @@ def run_ours(args):
     value = world * n * nsig * order * args.steps / t_dev
 
     # ---- end to end through the public API with host buffers
-    xh = torch.empty((n, nsig), dtype=torch.float32).pin_memory()
-    xh.copy_(x)
-    for _ in range(2):
-        yh = run_host(xh)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        yh = run_host(xh)
-    torch.cuda.synchronize()
-    t_all = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_all.item())
-    e2e_value = world * n * nsig * order * args.steps / t_e2e
-    assert tuple(yh.shape) == (n, nsig) and not yh.is_cuda
+    e2e_value, t_e2e = None, float("nan")
+    if args.workload == "config2":             # the record runs of the big configs skip it
+        xh = torch.empty((n, nsig), dtype=torch.float32).pin_memory()
+        xh.copy_(x)
+        for _ in range(2):
+            yh = run_host(xh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            yh = run_host(xh)
+        torch.cuda.synchronize()
+        t_all = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_all.item())
+        e2e_value = world * n * nsig * order * args.steps / t_e2e
+        assert tuple(yh.shape)[:2] == (n, nsig) and not yh.is_cuda
 
     nnz_all = torch.tensor([nnz], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -382,12 +407,12 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (one fused step, k >= 2), per GPU
-    b_first, b_step, b_call = algorithmic_bytes(n, nnz, nsig, 1, order)
+    b_first, b_step, b_call = algorithmic_bytes(n, nnz, nsig, wl["nscales"], order)
     peak, peak_src = measured_peak()
     achieved = b_call * args.steps / t_dev / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(), "per_gpu": True,
-                "kernel": "cheby_step_tiled<16,1,false> (TMA-tiled fused step)",
+                "kernel": "cheby_step_tiled (TMA-tiled fused step, csrc/cheby_tiled.cu)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b_step,
                 "avg_launch_ms": 1e3 * t_dev / args.steps * (b_step / b_call),
                 "timing": "CUDA events on the launching stream over the timed region, max over ranks"}
@@ -406,7 +431,7 @@ def run_ours(args):
         xs = x[:, :cols].double().cpu().numpy()
         t_cpu = cpu_reference_time(Lh, lmax, c, xs, 1)
         ref = orc.cheby_op(Lh, lmax, c, xs[:, :1])
-        got = apx.cheby_op_device(L, lmax, c, x[:, :1].contiguous())[0].cpu().numpy()
+        got = apx.cheby_op_device(L, lmax, c, x[:, :1].contiguous()).reshape(-1, 1).cpu().numpy()
         parity = float(np.abs(got - ref).max() / np.abs(ref).max())
         cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                "host_cores_available": os.cpu_count(),
@@ -427,8 +452,11 @@ def run_ours(args):
                       "l2_policy": "inputs_exceed_l2 (working set %.2f GB per GPU per call >> 126 MB)"
                                    % ((4 * n * nsig * 4 + 8 * nnz) / 1e9)},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * nsig * world,
-                   "d2h_bytes_per_step": 4 * n * nsig * world, "ms_per_step": 1e3 * t_e2e / args.steps,
-                   "api": "Heat(G, 50).filter(pinned_host_tensor, order=30)" if world == 1 else
+                   "d2h_bytes_per_step": 4 * n * nsig * world * wl["nscales"],
+                   "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "api": "%s.filter(pinned_host_tensor, order=%d)" % (
+                       "MexicanHat(G, Nf=6)" if wl["bank"] == "mexicanhat" else "Heat(G, 50)", order)
+                   if world == 1 else
                           "PartitionedCheby.cheby_op(pinned host block -> H2D -> op -> D2H)"},
            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "halo": halo,
            "clocks": clocks.summary(t_region0, t_region1)}
