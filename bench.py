@@ -416,6 +416,13 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b_step,
                 "avg_launch_ms": 1e3 * t_dev / args.steps * (b_step / b_call),
                 "timing": "CUDA events on the launching stream over the timed region, max over ranks"}
+    # for a graph without locality the x_cur term of the algorithmic bytes
+    # (each row once) is unattainable; the gather-aware figure charges every stored entry
+    # one neighbour-row read of max(32, 4*nsig) bytes instead (no reuse at all).
+    gather = nnz * max(32, 4 * nsig) - 4 * n * nsig
+    roofline["gather_aware"] = {"bytes_per_launch": b_step + gather,
+                                "frac_if_no_gather_reuse": (b_call + order * gather) * args.steps
+                                / t_dev / 1e9 / peak}
     if halo is not None:
         halo_bytes = halo["rows_received_per_rank"] * nsig * 4
         halo.update({"bytes_received_per_rank_per_step": halo_bytes,
