@@ -179,23 +179,59 @@ def ncu_traffic():
 
 # -------------------------------------------------------------- CPU reference
 _REF = {}          # inherited by the forked workers: nothing big is pickled per task
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _import_reference():
+    """The unmodified PyGSP 0.6.1, pip-installed offline into baseline/_ref (git-ignored,
+    travels with the snapshot): `pip install --no-index --no-deps --target baseline/_ref
+    /root/reference`.  None when absent -- the oracle port then stands in."""
+    if not os.path.isdir(os.path.join(REF_DIR, "pygsp")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import logging
+        import pygsp
+        logging.getLogger("pygsp").setLevel(logging.ERROR)
+        return pygsp
+    except Exception:
+        return None
 
 
 def _cpu_worker(cols):
-    from oracle import pygsp_oracle as orc
     lo, hi = cols
-    orc.cheby_op(_REF["L"], _REF["lmax"], _REF["c"], _REF["x"][:, lo:hi])
+    x = _REF["x"][:, lo:hi]
+    if _REF["kind"] == "reference":
+        _REF["filter"].filter(x, method="chebyshev", order=_REF["order"])   # stock PyGSP path
+    else:
+        from oracle import pygsp_oracle as orc
+        orc.cheby_op(_REF["L"], _REF["lmax"], _REF["c"], x)
     return hi - lo
 
 
 class CpuReference:
-    """The oracle port (scipy csr_matvecs + numpy, float64 -- the reference's own
-    arithmetic, approximations.py:58-114) with the signal columns sharded over
-    `procs` forked processes (the reference itself is single-threaded)."""
+    """The reference's CPU path on `procs` host processes.
 
-    def __init__(self, L, lmax, c, x, procs):
+    kind 'reference': the real `pygsp.filters.Heat(G, scale).filter(x, order=...)` (scipy
+    csr_matvecs + numpy, float64, single-threaded by construction) with the signal columns
+    sharded over forked processes; kind 'port': the oracle restatement of the same
+    arithmetic when baseline/_ref is not there."""
+
+    def __init__(self, W, lmax, scale, order, x, procs):
         import multiprocessing as mp
-        _REF.update(L=L, lmax=lmax, c=c, x=np.ascontiguousarray(x))
+        pygsp = _import_reference()
+        _REF.clear()
+        _REF.update(lmax=lmax, order=order, x=np.ascontiguousarray(x))
+        if pygsp is not None:
+            G = pygsp.graphs.Graph(W)
+            G._lmax, G._lmax_method = float(lmax), "lanczos"      # same lmax on both sides
+            _REF.update(kind="reference", filter=pygsp.filters.Heat(G, scale=scale))
+        else:
+            from oracle import pygsp_oracle as orc
+            _REF.update(kind="port", L=orc.laplacian(W),
+                        c=orc.cheby_coeff(orc.heat_kernels(lmax, scale), lmax, order))
+        self.kind = _REF["kind"]
         self.procs = max(1, min(procs, x.shape[1]))
         edges = np.linspace(0, x.shape[1], self.procs + 1).astype(int)
         self.chunks = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
@@ -215,14 +251,6 @@ class CpuReference:
             self.pool.join()
 
 
-def cpu_reference_time(L, lmax, c, x, procs):
-    ref = CpuReference(L, lmax, c, x, procs)
-    try:
-        return ref.time_once()
-    finally:
-        ref.close()
-
-
 def run_reference(args):
     """--impl reference: the reference's CPU path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -235,27 +263,27 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
     W = host_graph(wl["N"], wl["k"], wl["seed"])
-    L = orc.laplacian(W)
     lmax = orc.upper_bound(W)                  # estimate_lmax(method="bounds"): deterministic
-    c = orc.cheby_coeff(orc.heat_kernels(lmax, wl["scale"]), lmax, wl["order"])
     ncols = min(wl["nsig"], procs)              # bounded sample: one signal column per process
     x = np.random.default_rng(0).standard_normal((wl["N"], ncols))
-    ref = CpuReference(L, lmax, c, x, procs)
+    ref = CpuReference(W, lmax, wl["scale"], wl["order"], x, procs)
     for _ in range(min(args.warmup, 1)):
         ref.time_once()
     times = [ref.time_once() for _ in range(args.steps)]
     ref.close()
     t = float(np.sum(times))
     value = wl["N"] * ncols * wl["order"] * args.steps / t
-    sample = "%d of %d signal columns per step (one per process), full graph, full order" % (
-        ncols, wl["nsig"])
+    what = ("unmodified PyGSP 0.6.1 from baseline/_ref, Heat(G, 50).filter(x, order=30)"
+            if ref.kind == "reference" else "oracle port of approximations.cheby_op")
+    sample = "%d of %d signal columns per step (one per process), full graph, full order; %s" % (
+        ncols, wl["nsig"], what)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": wl["name"], **{k: wl[k] for k in
-                                        ("N", "k", "nsig", "order")}, "nnz_L": int(L.nnz)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                                        ("N", "k", "nsig", "order")}, "nnz_W": int(W.nnz)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.procs, "kind": ref.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -436,14 +464,21 @@ def run_ours(args):
         cols = args.cpu_columns
         Lh = L.to_scipy().astype(np.float64)
         xs = x[:, :cols].double().cpu().numpy()
-        t_cpu = cpu_reference_time(Lh, lmax, c, xs, 1)
+        if wl["bank"] == "heat":
+            cref = CpuReference(G.W.to_scipy().astype(np.float64), lmax, wl["scale"], order, xs, 1)
+            t_cpu, cpu_kind = cref.time_once(), cref.kind
+        else:                                   # banks: time the oracle port of cheby_op
+            t0 = time.perf_counter()
+            orc.cheby_op(Lh, lmax, c, xs)
+            t_cpu, cpu_kind = time.perf_counter() - t0, "port"
         ref = orc.cheby_op(Lh, lmax, c, xs[:, :1])
         got = apx.cheby_op_device(L, lmax, c, x[:, :1].contiguous()).reshape(-1, 1).cpu().numpy()
         parity = float(np.abs(got - ref).max() / np.abs(ref).max())
-        cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                "host_cores_available": os.cpu_count(),
-               "sample": "%d of %d signal columns, full graph, full order, float64 scipy "
-                         "csr_matvecs + numpy (oracle port), best of 1" % (cols, nsig),
+               "sample": "%d of %d signal columns, full graph, full order, float64; %s" % (
+                   cols, nsig, "unmodified PyGSP 0.6.1 (baseline/_ref) g.filter()"
+                   if cpu_kind == "reference" else "oracle port (scipy csr_matvecs + numpy)"),
                "parity_rel_err_vs_gpu": parity}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -12,6 +12,7 @@ from .. import _native as nat
 from .. import utils
 
 _logger = utils.build_logger(__name__)
+PATCH_DEFAULT_DTYPE = None     # engine dtype for reference (scipy) graphs, see patch_pygsp()
 
 
 @utils.filterbank_handler
@@ -74,7 +75,7 @@ def _laplacian_on_device(G):
     torch = nat.require_cuda()
     cached = getattr(G, "_gspb200_L", None)
     if cached is None or cached[0] is not L:
-        dtype = getattr(G, "_gspb200_dtype", torch.float32)
+        dtype = getattr(G, "_gspb200_dtype", None) or PATCH_DEFAULT_DTYPE or torch.float32
         dev = torch.device("cuda:%d" % torch.cuda.current_device())
         cached = (L, DeviceCSR.from_scipy(L, dtype, dev))
         G._gspb200_L = cached
@@ -165,7 +166,10 @@ def cheby_op(G, c, signal, **kwargs):
     r = r.reshape(c.shape[0] * G.N, x.shape[1])
     if one_d:
         r = r.reshape(-1)
-    return _leave_device(r, kind)
+    out = _leave_device(r, kind)
+    if kind == "numpy" and not isinstance(G.L, type(L)):
+        out = out.astype(np.float64, copy=False)     # a reference graph expects float64 back
+    return out
 
 
 class _GraphView:
