@@ -24,4 +24,4 @@ def pytest_configure(config):
 
 
 def pytest_unconfigure(config):
-    print("\\nGSPB200_ENGINE_CALLS=%d" % CALLS["n"])
+    print("\nGSPB200_ENGINE_CALLS=%d" % CALLS["n"])
