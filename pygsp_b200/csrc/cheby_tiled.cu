@@ -428,12 +428,15 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   memset(plan, 0, sizeof(*plan));
   const char* force = getenv("GSPB200_KERNEL");
   if (force && strcmp(force, "rowgroup") == 0) return GSP_OK;
-  if (!(nsig == 32 || nsig == 64 || nsig == 128)) return GSP_OK;
+  if (!(nsig == 8 || nsig == 16 || nsig == 32 || nsig == 64 || nsig == 128)) return GSP_OK;
   if (nscales < 0 || nscales > kTiledMaxScales) return GSP_OK;
   // vector tiles per stage: x_old + one r tile per scale; keep a stage near 40 KB
   int R = env_int("GSPB200_TILE_R", nscales <= 1 ? 64 : (nscales <= 2 ? 32 : 16));
   if (nsig == 128) R = std::max(8, R / 2);
   R = std::max(8, (R / 8) * 8);
+  const int warps_default = 16;
+  // narrow blocks: a warp carries 32 / (nsig/4) rows, a tile should feed every warp
+  if (nsig <= 16 && !getenv("GSPB200_TILE_R")) R = std::max(R, warps_default * (128 / (int)nsig));
   const int64_t n_tiles = n / R;
   if (n_tiles < 1) return GSP_OK;
   int* dmax = nullptr;
@@ -542,11 +545,13 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
     a.half_c0[i] = (first && i < nscales) ? float(0.5 * c0[i]) : 0.f;
   }
   switch (nsig) {
+    case 8: return launch_tiled_g<2>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
+    case 16: return launch_tiled_g<4>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
     case 32: return launch_tiled_g<8>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
     case 64: return launch_tiled_g<16>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
     case 128: return launch_tiled_g<32>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
   }
-  return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 32, 64 or 128 (%s)", "nsig");
+  return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 8, 16, 32, 64 or 128 (%s)", "nsig");
 }
 
 }  // namespace gsp
