@@ -60,9 +60,8 @@ def lib():
     """Load (building in-tree if needed) the shared library."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if not os.path.exists(path) or os.environ.get("GSPB200_REBUILD"):
-            path = _build.build()
+        # rebuilds only when the sources' hash differs from the one the .so was built from
+        path = _build.build(force=bool(os.environ.get("GSPB200_REBUILD")))
         try:
             _lib = ctypes.CDLL(path)
         except OSError as exc:   # pragma: no cover
