@@ -49,6 +49,7 @@ struct TileArgs {
   float ck[kTiledMaxScales];
   gsp_halo_fusion halo;   // all zero when the step does not exchange a halo
   int l2_hint;            // evict-first hint on the streamed TMA copies
+  int stage_xcur;         // stage the tile's own x_cur rows (XS variant)
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
 };
 
@@ -119,8 +120,11 @@ struct TileLayout {
   int ptr_bytes;      // indptr slab + trailing slot
   int stage_bytes;
   int bar_bytes;
-  __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages) {
-    vec_bytes = first ? 0 : (1 + nscales) * R * nsig * 4;
+  int xs_offset;      // float offset of the staged x_cur tile inside the vec area
+  __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages,
+                                 bool xs = false) {
+    xs_offset = first ? 0 : (1 + nscales) * R * nsig;
+    vec_bytes = (xs_offset + (xs ? R * nsig : 0)) * 4;
     slab_bytes = (cap + 16) * 4;                // +16: aligned groups may run past the end
     ptr_bytes = (R + 4) * 4;
     stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;   // +16: slab offset, group counter
@@ -129,15 +133,17 @@ struct TileLayout {
   __host__ __device__ int total(int stages) const { return bar_bytes + stages * stage_bytes; }
 };
 
-template <int G, int U, bool FIRST, int NSC, bool BIG>
-__global__ void __launch_bounds__(BIG ? 1024 : 32 * 17, (BIG || U != 1) ? 1 : 2)
+// XS: the tile's own x_cur rows are staged too and neighbours that fall inside the tile
+// are read from shared memory instead of L1 (experimental, GSPB200_TILE_XS=1).
+template <int G, int U, bool FIRST, int NSC, bool XS>
+__global__ void __launch_bounds__(32 * 17, U != 1 ? 1 : 2)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.rows_per_tile;
   const int S = a.stages;
   const int NW = a.consumer_warps;
   const int nsig = a.nsig;
-  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S);
+  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S, XS);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + S;
   unsigned char* stage0 = smem + lay.bar_bytes;
@@ -209,9 +215,11 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       }
       const uint32_t slab = a1 > a0 ? uint32_t(a1 - a0) * 4u : 0u;
       const uint32_t tile_vec = uint32_t(R) * nsig * 4u;
-      const uint32_t bytes = uint32_t(R) * 4u + 2u * slab + (FIRST ? 0u : tile_vec * (1 + a.nscales));
+      const uint32_t bytes = uint32_t(R) * 4u + 2u * slab +
+                             (FIRST ? 0u : tile_vec * (1 + a.nscales)) + (XS ? tile_vec : 0u);
       mbar_expect_tx(full + s, bytes);
       bulk_g2s(sm_ptr, a.indptr + r0, uint32_t(R) * 4u, full + s);
+      if (XS) bulk_g2s(sm_vec + lay.xs_offset, a.x_cur + r0 * nsig, tile_vec, full + s);
       if (hint) {
         if (slab) {
           bulk_g2s_hint(sm_col, a.indices + a0, slab, full + s, pol);
@@ -261,6 +269,8 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     const int a0 = sm_ptr[R + 4];
     const int64_t r0 = a.row_begin + tile * R;
     const bool push_tile = tile < a.halo.n_push_tiles;      // warp-uniform
+    const int tile_row0 = int(r0);
+    const float* sm_x = sm_vec + lay.xs_offset + c0;
     const float* __restrict__ xc_tile = xg + r0 * NS;
     float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
     float* __restrict__ r_tile = a.r + r0 * NS + c0;
@@ -271,7 +281,8 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
       const unsigned span = unsigned(je - jb);
-      const float4 xc = ldg_f4(xc_tile + off);
+      const float4 xc = XS ? *reinterpret_cast<const float4*>(sm_vec + lay.xs_offset + off + c0)
+                           : ldg_f4(xc_tile + off);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       // The slab offset a0 is a multiple of 4, so groups of four CSR entries are
       // 16-byte aligned in shared memory: one LDS.128 brings four column indices,
@@ -294,10 +305,19 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           ok[4 * u + 1] = unsigned(base + 1) < span;
           ok[4 * u + 2] = unsigned(base + 2) < span;
           ok[4 * u + 3] = unsigned(base + 3) < span;
-          if (ok[4 * u + 0]) xv[4 * u + 0] = ldg_f4(xg + int64_t(c4[u].x) * NS);
-          if (ok[4 * u + 1]) xv[4 * u + 1] = ldg_f4(xg + int64_t(c4[u].y) * NS);
-          if (ok[4 * u + 2]) xv[4 * u + 2] = ldg_f4(xg + int64_t(c4[u].z) * NS);
-          if (ok[4 * u + 3]) xv[4 * u + 3] = ldg_f4(xg + int64_t(c4[u].w) * NS);
+          const int cq[4] = {c4[u].x, c4[u].y, c4[u].z, c4[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (!ok[4 * u + q]) continue;
+            if (XS) {
+              const unsigned rel = unsigned(cq[q] - tile_row0);
+              if (rel < unsigned(R)) {
+                xv[4 * u + q] = *reinterpret_cast<const float4*>(sm_x + rel * NS);
+                continue;
+              }
+            }
+            xv[4 * u + q] = ldg_f4(xg + int64_t(cq[q]) * NS);
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -451,7 +471,7 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   cudaFreeAsync(dmax, st);
   const int cap = ((hmax + 8 + 31) / 32) * 32;
   int stages = env_int("GSPB200_TILE_S", nscales <= 1 ? 2 : 3);
-  const int warps = std::min(31, std::max(1, env_int("GSPB200_TILE_NW", 16)));
+  const int warps = std::min(16, std::max(1, env_int("GSPB200_TILE_NW", 16)));
   // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
   const int budget = env_int("GSPB200_TILE_SMEM", 100 * 1024);
   TileLayout lay(R, cap, (int)nsig, nscales, false, stages);
@@ -466,12 +486,12 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   return GSP_OK;
 }
 
-template <int G, int U, int NSC, bool BIG>
+template <int G, int U, int NSC, bool XS>
 static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
-  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages);
+  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages, XS);
   const int smem = lay.total(a.stages);
   const int threads = 32 * (1 + a.consumer_warps);
-  auto kern = first ? cheby_step_tiled<G, U, true, NSC, BIG> : cheby_step_tiled<G, U, false, NSC, BIG>;
+  auto kern = first ? cheby_step_tiled<G, U, true, NSC, XS> : cheby_step_tiled<G, U, false, NSC, XS>;
   GSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
   GSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -483,26 +503,22 @@ static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cuda
   return GSP_OK;
 }
 
-template <int G, int U, bool BIG>
+template <int G, int U, bool XS>
 static int launch_tiled_gu(bool first, const TileArgs& a, int bps, cudaStream_t st) {
   switch (a.nscales) {          // common bank widths get the scale loop unrolled
-    case 0: return launch_tiled_k<G, U, 0, BIG>(first, a, bps, st);
-    case 1: return launch_tiled_k<G, U, 1, BIG>(first, a, bps, st);
-    case 2: return launch_tiled_k<G, U, 2, BIG>(first, a, bps, st);
-    default: return launch_tiled_k<G, U, -1, BIG>(first, a, bps, st);
+    case 0: return launch_tiled_k<G, U, 0, XS>(first, a, bps, st);
+    case 1: return launch_tiled_k<G, U, 1, XS>(first, a, bps, st);
+    case 2: return launch_tiled_k<G, U, 2, XS>(first, a, bps, st);
+    default: return launch_tiled_k<G, U, -1, XS>(first, a, bps, st);
   }
 }
 
 template <int G>
 static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cudaStream_t st) {
   // `unroll` = neighbour packets requested back to back: 4 or 8 (groups of four entries)
-  const bool big = a.consumer_warps > 16;
-  if (unroll >= 8) {
-    return big ? launch_tiled_gu<G, 2, true>(first, a, bps, st)
-               : launch_tiled_gu<G, 2, false>(first, a, bps, st);
-  }
-  return big ? launch_tiled_gu<G, 1, true>(first, a, bps, st)
-             : launch_tiled_gu<G, 1, false>(first, a, bps, st);
+  if (unroll >= 8) return launch_tiled_gu<G, 2, false>(first, a, bps, st);
+  return a.stage_xcur ? launch_tiled_gu<G, 1, true>(first, a, bps, st)
+                      : launch_tiled_gu<G, 1, false>(first, a, bps, st);
 }
 
 // Full tiles of rows [rb, re) of one step (rb % 4 == 0); reports the number of rows done.
@@ -515,6 +531,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
   TileArgs a;
   a.add_source = add_source ? 1 : 0;
   a.l2_hint = env_int("GSPB200_TILE_HINT", 1);
+  a.stage_xcur = env_int("GSPB200_TILE_XS", 0);
   GSP_REQUIRE(!add_source || (nscales >= 1 && !first), "add_source needs source blocks");
   memset(&a.halo, 0, sizeof(a.halo));
   if (halo) {

@@ -245,6 +245,79 @@ class PartitionedCheby:
         out[:, self.perm] = r
         return out
 
+    # ------------------------------------------------------------------- lmax
+    def spmv(self, v):
+        """(L v) restricted to this rank's rows; v: (n_local,) in local order."""
+        import torch
+        p = self.plan
+        buf = torch.empty((p.n_local + p.n_halo, 1), dtype=self.dtype, device=self.device)
+        buf[:p.n_local, 0] = v
+        self._exchange(buf, 1)
+        return self.backend.spmm(self, buf)[:, 0]
+
+    def estimate_lmax(self, method="lanczos", seed=0, tol=5e-3, max_steps=400, polish_steps=60):
+        """Distributed ``Graph.estimate_lmax`` (graph.py:858-931) for the partitioned L.
+
+        'lanczos': the same three-term recurrence and stopping rule as the single-GPU
+        engine (``graphs.graph.ritz_check``); the operator is the local SpMM after a halo
+        exchange, the two scalars per step are all-reduced.  Returns 1.01 * theta.
+        'bounds': Gershgorin bound 2 max_i L_ii over all ranks (graph.py:943-945).
+        """
+        import torch
+        import torch.distributed as dist
+        from .graphs.graph import ritz_check
+        p = self.plan
+
+        def allsum(t):
+            if p.parts > 1:
+                dist.all_reduce(t, group=self.group)
+            return t
+        if method == "bounds":
+            rows = torch.arange(p.n_local, device=self.device)
+            diag = torch.zeros(p.n_local, dtype=torch.float64, device=self.device)
+            ptr = self.indptr.long()
+            row_of = torch.repeat_interleave(rows, ptr[1:] - ptr[:-1])
+            on_diag = self.indices.long() == row_of
+            diag.index_add_(0, row_of[on_diag], self.data[on_diag].double())
+            top = 2.0 * diag.max().reshape(1) if p.n_local else torch.zeros(1, dtype=torch.float64,
+                                                                            device=self.device)
+            if p.parts > 1:
+                dist.all_reduce(top, op=dist.ReduceOp.MAX, group=self.group)
+            return float(top.item())
+        if method != "lanczos":
+            raise ValueError("Unknown method {}".format(method))
+        gen = torch.Generator(device=self.device).manual_seed(seed * 7919 + p.rank)
+        v = torch.rand(p.n_local, device=self.device, dtype=torch.float64, generator=gen) * 2 - 1
+        v = (v / allsum((v * v).sum().reshape(1)).sqrt()).to(self.dtype)
+        v_prev, beta_prev = None, 0.0
+        alphas, betas = [], []
+        cap = int(min(p.n_global, max_steps))
+        theta, converged = 0.0, False
+        for j in range(cap):
+            w = self.spmv(v).double()
+            alpha = float(allsum((w * v.double()).sum().reshape(1)).item())
+            w = w - alpha * v.double()
+            if v_prev is not None:
+                w = w - beta_prev * v_prev.double()
+            beta = float(allsum((w * w).sum().reshape(1)).sqrt().item())
+            alphas.append(alpha)
+            betas.append(beta)
+            done = j + 1
+            if done >= 10 and (done - 10) % 5 == 0 or done == cap or beta == 0.0:
+                theta, _, stop, ref_rule = ritz_check(np.array(alphas), np.array(betas), tol,
+                                                      self.dtype == torch.float32,
+                                                      done >= polish_steps)
+                converged = converged or ref_rule
+                if stop:
+                    return 1.01 * theta
+            if beta == 0.0:
+                break
+            v_prev, beta_prev = v, beta
+            v = (w / beta).to(self.dtype)
+        if converged or cap == p.n_global:
+            return 1.01 * theta
+        raise ValueError("The Lanczos method did not converge. Try to use bounds.")
+
     def _cheby_op_p2p(self, lmax, c, x, local_order):
         """Same recurrence; the halo travels by peer stores + flags (see PeerWindow)."""
         import torch
@@ -491,6 +564,16 @@ class _CudaBackend:
                      nat.i64(op.plan.n_local), nat.i64(nsig), nat.i32(nscales), ck, c0,
                      nat.f64(coef[0]), nat.f64(coef[1]), nat.f64(coef[2]), plan,
                      nat.stream_ptr(self.device))
+
+    def spmm(self, op, x_ext):
+        """y = L_local x_ext: (n_local, width) from the extended (n_local + n_halo, width)."""
+        torch = nat.require_cuda()
+        width = int(x_ext.shape[1])
+        y = torch.empty((op.plan.n_local, width), dtype=op.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.call("gsp_spmm_" + nat.suffix(op.dtype), nat.i64(op.plan.n_local), op.indptr,
+                     op.indices, op.data, x_ext, nat.i64(width), y, nat.stream_ptr(self.device))
+        return y
 
     def step_halo(self, op, first, x_cur, x_old, x_new, r, nsig, nscales, ck, c0, coef, plan, halo):
         torch = nat.require_cuda()

@@ -321,7 +321,6 @@ class Graph:
         eigenvalue error estimate resid^2 / (theta_1 - theta_2) is below 1e-5 |theta|
         or ``polish_steps`` products have been spent.
         """
-        from scipy.linalg import eigh_tridiagonal
         torch = nat.require_cuda()
         n, L = self.n_vertices, self.L
         if n == 0 or L.nnz == 0:
@@ -338,25 +337,11 @@ class Graph:
                        nat.i32(done), nat.i32(nxt), nat.i32(cap), nat.u64(seed), scal)
             done = nxt
             host = scal.cpu().numpy()
-            alpha, beta = host[:done], host[cap:cap + done]
-            scale = max(np.abs(alpha).max(), np.abs(beta).max(), 1e-300)
-            # beta_j ~ 0: v_0..v_j span an invariant subspace, T_{j+1} is exact and
-            # what follows would be round-off; stop there (residual <= beta_j).
-            floor = (1e-5 if self._sfx == "f32" else 1e-12) * scale
-            tiny = np.flatnonzero(beta <= floor)
-            m = int(tiny[0]) + 1 if tiny.size else done
-            if m == 1:
-                theta, second, last = float(alpha[0]), None, 1.0
-            else:
-                w, v = eigh_tridiagonal(alpha[:m], beta[:m - 1])
-                theta, second, last = float(w[-1]), float(w[-2]), abs(float(v[-1, -1]))
-            resid = float(beta[m - 1]) * last
+            theta, m, stop, ref_rule = ritz_check(host[:done], host[cap:cap + done], tol,
+                                                  self._sfx == "f32", done >= polish_steps)
             self._lanczos_steps = m
-            ref_rule = resid <= tol * max(abs(theta), np.finfo(float).eps ** (2.0 / 3))
             converged = converged or ref_rule
-            gap = max(theta - second, resid) if second is not None else resid
-            tight = resid == 0 or resid * resid / max(gap, 1e-300) <= 1e-5 * abs(theta)
-            if tiny.size or (ref_rule and (tight or done >= polish_steps)):
+            if stop:
                 return theta
         if converged or cap == n:   # cap == n: the Krylov space is the whole space
             return theta
@@ -390,6 +375,33 @@ class Graph:
         raise NotImplementedError(
             "The dense eigendecomposition (pygsp/graphs/fourier.py) is outside the Chebyshev "
             "filtering path this engine implements; use estimate_lmax().")
+
+
+def ritz_check(alpha, beta, tol, single_precision, polish_done):
+    """Largest Ritz value of the Lanczos tridiagonal matrix and whether to stop.
+
+    alpha[0..m), beta[0..m): recurrence coefficients so far (beta[j] couples v_j, v_j+1).
+    Returns (theta, steps_used, stop).  Stop rule: the reference's (|beta_m s_m| <=
+    tol |theta|, graph.py:911-917) and then either the eigenvalue error estimate
+    resid^2 / (theta_1 - theta_2) <= 1e-5 |theta| or ``polish_done``; an (almost) zero
+    beta_j means an invariant subspace (T_{j+1} exact) and stops at once.
+    """
+    from scipy.linalg import eigh_tridiagonal
+    done = len(alpha)
+    scale = max(np.abs(alpha).max(), np.abs(beta).max(), 1e-300)
+    floor = (1e-5 if single_precision else 1e-12) * scale
+    tiny = np.flatnonzero(beta <= floor)
+    m = int(tiny[0]) + 1 if tiny.size else done
+    if m == 1:
+        theta, second, last = float(alpha[0]), None, 1.0
+    else:
+        w, v = eigh_tridiagonal(alpha[:m], beta[:m - 1])
+        theta, second, last = float(w[-1]), float(w[-2]), abs(float(v[-1, -1]))
+    resid = float(beta[m - 1]) * last
+    ref_rule = resid <= tol * max(abs(theta), np.finfo(float).eps ** (2.0 / 3))
+    gap = max(theta - second, resid) if second is not None else resid
+    tight = resid == 0 or resid * resid / max(gap, 1e-300) <= 1e-5 * abs(theta)
+    return theta, m, bool(tiny.size or (ref_rule and (tight or polish_done))), ref_rule
 
 
 def symmetrize_average_device(W):

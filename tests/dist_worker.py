@@ -28,6 +28,12 @@ class NumpyBackend:
     def gather_rows(self, buf, idx, nsig):
         return buf.index_select(0, idx).contiguous()
 
+    def spmm(self, op, x_ext):
+        import torch
+        from oracle import pygsp_oracle as orc
+        return torch.from_numpy(orc.csr_spmm(op.indptr.numpy().astype(np.int64), op.indices.numpy(),
+                                             op.data.numpy(), x_ext.numpy()))
+
     def step(self, op, first, x_cur, x_old, x_new, r, nsig, nscales, ck, c0, coef, plan, rows):
         from oracle import pygsp_oracle as orc
         rb, re = rows
@@ -101,6 +107,11 @@ def main():
         op = gd.PartitionedCheby(plan, dtype=dtype, backend=NumpyBackend())
         xl = torch.from_numpy(x[lo:hi].copy())
         tol = 1e-12
+    # distributed lmax: brackets the true eigenvalue like the single-process estimate
+    lam = orc.lambda_max_exact(L)
+    est = op.estimate_lmax()
+    assert lam * (1 - 2e-4) <= est / 1.01 <= lam * (1 + 1e-5), (est, lam)
+    assert op.estimate_lmax(method="bounds") >= lam
     r = op.cheby_op(lmax, c, xl).cpu().numpy().astype(np.float64)
     want = ref[:, lo:hi]
     err = np.abs(r - want).max() / np.abs(ref).max()
