@@ -204,7 +204,15 @@ class PartitionedCheby:
         nsig = int(x.shape[1])
         n, nb = p.n_local, p.n_boundary
         ext = n + p.n_halo
-        mode = self.exchange or ("p2p" if self.backend.has_streams and p.parts > 1 else "nccl")
+        # Small halos (k-NN / grid cuts: < 1 MB): the exchange fused into the step kernel
+        # wins (7.58 vs 7.89 ms on 2 GPUs).  Huge halos (SBM: 588 MB per step): one packed
+        # NCCL transfer overlapped with the interior rows beats 128-byte peer stores
+        # (95.7 vs 109.2 ms).  Measured on 2 x B200, profiles/r1_bench_*n2*.json.
+        halo_bytes = p.n_halo * nsig * torch.empty((), dtype=self.dtype).element_size()
+        mode = self.exchange
+        if mode is None:
+            mode = "p2p" if (self.backend.has_streams and p.parts > 1 and
+                             halo_bytes < self.overlap_min_bytes) else "nccl"
         if mode == "p2p":
             return self._cheby_op_p2p(lmax, c, x, local_order)
         bufs = [torch.empty((ext, nsig), dtype=self.dtype, device=self.device) for _ in range(2)]
