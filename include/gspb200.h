@@ -143,6 +143,9 @@ int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, co
                     void* stream);
 
 /* ------------------------------------------------------------------ graph ---
+ * gsp_coo_to_csr_*    graph.py:109  sparse.csr_matrix(coo): sort by (row, col), sum duplicates.
+ *     indices / data are sized nnz by the caller; the number of distinct entries comes back
+ *     in *n_unique_host_out (the call synchronises the stream once).
  * gsp_csr_inspect_*   graph.py:111-122  NaN / Inf / negative / self-loop checks.
  *     stats_dev[8] (int64): [0] NaN [1] Inf [2] negative [3] non-zero diagonal
  *     [4] stored zeros [5] unsorted-or-duplicate columns [6] column out of range.
@@ -222,6 +225,9 @@ int gsp_knn_to_csr_f64(int64_t n, int k, const int32_t* nn_idx, const double* nn
   int gsp_csr_transpose_##SUF(int64_t n, int64_t nnz, const int32_t* indptr,                     \
                               const int32_t* indices, const T* data, int32_t* t_indptr,          \
                               int32_t* t_indices, T* t_data, void* stream);                      \
+  int gsp_coo_to_csr_##SUF(int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols,      \
+                           const T* vals, int32_t* indptr, int32_t* indices, T* data,             \
+                           int64_t* n_unique_host_out, void* stream);                            \
   int gsp_csr_average_count_##SUF(int64_t n, const int32_t* a_indptr, const int32_t* a_indices,  \
                                   const T* a_data, const int32_t* b_indptr,                      \
                                   const int32_t* b_indices, const T* b_data, int32_t* s_indptr,  \

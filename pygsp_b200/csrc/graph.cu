@@ -181,6 +181,74 @@ static int csr_transpose(int64_t n, int64_t nnz, const int32_t* indptr, const in
   return scan_rows(t_indptr, n, st);
 }
 
+// ---- COO -> canonical CSR (sparse.csr_matrix(coo): duplicates summed, rows sorted) ----
+__global__ void coo_keys_kernel(int64_t nnz, const int32_t* __restrict__ rows,
+                                const int32_t* __restrict__ cols, int64_t n, uint64_t* keys,
+                                int* bad) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int r = rows[k], c = cols[k];
+  if (r < 0 || r >= n || c < 0 || c >= n) atomicAdd(bad, 1);
+  keys[k] = (uint64_t(uint32_t(r)) << 32) | uint32_t(c);
+}
+
+__global__ void coo_unpack_kernel(int64_t nuniq, const uint64_t* __restrict__ keys,
+                                  int32_t* indices, int32_t* indptr) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= nuniq) return;
+  indices[k] = int32_t(uint32_t(keys[k] & 0xffffffffu));
+  atomicAdd(indptr + int32_t(keys[k] >> 32) + 1, 1);
+}
+
+// Sorts by (row, col), sums duplicates; writes indptr and the first *n_unique_out
+// entries of indices / data (both sized nnz by the caller).  Synchronises the stream
+// once to return the number of distinct entries.
+template <typename T>
+static int coo_to_csr(int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols,
+                      const T* vals, int32_t* indptr, int32_t* indices, T* data,
+                      int64_t* n_unique_out, cudaStream_t st) {
+  GSP_CUDA(cudaMemsetAsync(indptr, 0, sizeof(int32_t) * (n + 1), st));
+  *n_unique_out = 0;
+  if (nnz == 0) return GSP_OK;
+  uint64_t *k0 = nullptr, *k1 = nullptr, *ku = nullptr;
+  T* v1 = nullptr;
+  int* scal = nullptr;       // [0] bad indices, [1] number of unique keys
+  GSP_CUDA(cudaMallocAsync((void**)&k0, 8 * nnz, st));
+  GSP_CUDA(cudaMallocAsync((void**)&k1, 8 * nnz, st));
+  GSP_CUDA(cudaMallocAsync((void**)&ku, 8 * nnz, st));
+  GSP_CUDA(cudaMallocAsync((void**)&v1, sizeof(T) * nnz, st));
+  GSP_CUDA(cudaMallocAsync((void**)&scal, 2 * sizeof(int), st));
+  GSP_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(int), st));
+  const int nb = (int)ceil_div(nnz, 256);
+  coo_keys_kernel<<<nb, 256, 0, st>>>(nnz, rows, cols, n, k0, scal);
+  int bits = 33;
+  while ((int64_t(1) << (bits - 32)) < n && bits < 64) ++bits;
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, vals, v1, (int)nnz, 0, bits, st);
+  cub::DeviceReduce::ReduceByKey(nullptr, b2, k1, ku, v1, data, scal + 1, cub::Sum(), (int)nnz, st);
+  void* tmp = nullptr;
+  const size_t bytes = std::max(b1, b2);
+  GSP_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, b1, k0, k1, vals, v1, (int)nnz, 0, bits, st);
+  if (e == cudaSuccess)
+    e = cub::DeviceReduce::ReduceByKey(tmp, b2, k1, ku, v1, data, scal + 1, cub::Sum(), (int)nnz, st);
+  int host[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, scal, sizeof(host), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && host[0] == 0) {
+    coo_unpack_kernel<<<(int)ceil_div(host[1] > 0 ? host[1] : 1, 256), 256, 0, st>>>(host[1], ku,
+                                                                                    indices, indptr);
+    e = cudaGetLastError();
+    note_launch(2);
+  }
+  cudaFreeAsync(tmp, st); cudaFreeAsync(k0, st); cudaFreeAsync(k1, st); cudaFreeAsync(ku, st);
+  cudaFreeAsync(v1, st); cudaFreeAsync(scal, st);
+  if (e != cudaSuccess) return check_cuda(e, "coo_to_csr");
+  if (host[0] != 0) return fail(GSP_ERR_ARG, "COO index out of range (%s)", "rows/cols");
+  *n_unique_out = host[1];
+  return scan_rows(indptr, n, st);
+}
+
 // ---- S = (A + B)/2 with exact-zero results dropped (utils.py:247-248) ----------
 template <typename T, bool FILL>
 __global__ void csr_average_kernel(int64_t n, const int32_t* __restrict__ a_ptr,
@@ -476,6 +544,13 @@ int move_rows(bool scatter, int64_t rows, const int64_t* idx, const T* src, int6
     GSP_REQUIRE(nnz < (int64_t(1) << 31), "nnz must fit int32");                                \
     return gsp::csr_transpose<T>(n, nnz, indptr, indices, data, t_indptr, t_indices, t_data,    \
                                  gsp::as_stream(stream));                                       \
+  }                                                                                             \
+  int gsp_coo_to_csr_##SUF(int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols,     \
+                           const T* vals, int32_t* indptr, int32_t* indices, T* data,            \
+                           int64_t* n_unique_host_out, void* stream) {                           \
+    GSP_REQUIRE(nnz < (int64_t(1) << 31) && n_unique_host_out, "nnz must fit int32");            \
+    return gsp::coo_to_csr<T>(n, nnz, rows, cols, vals, indptr, indices, data,                   \
+                              n_unique_host_out, gsp::as_stream(stream));                        \
   }                                                                                             \
   int gsp_csr_average_count_##SUF(int64_t n, const int32_t* a_indptr, const int32_t* a_indices, \
                                   const T* a_data, const int32_t* b_indptr,                     \

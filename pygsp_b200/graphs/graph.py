@@ -115,6 +115,36 @@ class Graph:
         self.compute_laplacian(lap_type)
         self.Ne = self.n_edges
 
+    @classmethod
+    def from_coo(cls, rows, cols, vals, n_vertices, lap_type="combinatorial", **kwargs):
+        """Graph from COO triplets already in HBM (int32 rows / cols, float values).
+
+        What ``sparse.csr_matrix(coo)`` does at graph.py:109 -- sort by (row, col), sum
+        duplicates -- runs on the device (``gsp_coo_to_csr_*``); no host matrix exists.
+        """
+        import ctypes
+        torch = nat.require_cuda()
+        dev = vals.device
+        dt = _torch_dtype(torch, kwargs.get("dtype", vals.dtype if vals.dtype in
+                                            (torch.float32, torch.float64) else None))
+        rows = rows.to(dev, torch.int32).contiguous()
+        cols = cols.to(dev, torch.int32).contiguous()
+        vals = vals.to(dev, dt).contiguous()
+        nnz = int(vals.numel())
+        indptr = torch.empty(n_vertices + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz, dtype=dt, device=dev)
+        uniq = ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            nat.call("gsp_coo_to_csr_" + nat.suffix(dt), nat.i64(n_vertices), nat.i64(nnz), rows,
+                     cols, vals, indptr, indices, data, ctypes.byref(uniq), nat.stream_ptr(dev))
+        m = int(uniq.value)
+        W = DeviceCSR(indptr, indices[:m].contiguous(), data[:m].contiguous(),
+                      (n_vertices, n_vertices))
+        kwargs.setdefault("dtype", dt)
+        kwargs.setdefault("device", dev)
+        return cls(W, lap_type=lap_type, **kwargs)
+
     # ------------------------------------------------------------------ basics
     @property
     def N(self):

@@ -509,6 +509,32 @@ def test_arbitrary_kernel_high_order(gsp, sensor5k):
     assert relerr_cols(y, ref) <= F32_TOL
 
 
+def test_graph_from_device_coo(gsp):
+    """COO -> CSR on the device == scipy.sparse.csr_matrix(coo) (graph.py:109)."""
+    import torch
+    from scipy import sparse
+    rng = np.random.default_rng(12)
+    n, m = 3000, 40000
+    r = rng.integers(0, n, m); c = rng.integers(0, n, m)
+    keep = r != c
+    r, c = r[keep], c[keep]
+    v = rng.uniform(0.1, 1.0, r.size)
+    rows = np.concatenate([r, c]); cols = np.concatenate([c, r]); vals = np.concatenate([v, v])
+    ref = sparse.csr_matrix(sparse.coo_matrix((vals, (rows, cols)), shape=(n, n)))   # sums duplicates
+    G = gsp.graphs.Graph.from_coo(torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(),
+                                  torch.from_numpy(vals).cuda(), n, dtype=np.float64)
+    W = G.W.to_scipy()
+    np.testing.assert_array_equal(W.indptr, ref.indptr)
+    np.testing.assert_array_equal(W.indices, ref.indices)
+    np.testing.assert_allclose(W.data, ref.data, rtol=1e-13)
+    assert not G.is_directed()
+    L = orc.laplacian(ref)
+    np.testing.assert_array_equal(G.L.to_scipy().indices, L.indices)
+    with pytest.raises(gsp._native.NativeError):
+        gsp.graphs.Graph.from_coo(torch.tensor([0, 5]).cuda(), torch.tensor([1, 0]).cuda(),
+                                  torch.tensor([1.0, 1.0]).cuda(), 3)
+
+
 def test_spmm_dot(gsp, sensor5k):
     G, L, _ = sensor5k
     x = np.random.default_rng(2).standard_normal((G.N, 10))
