@@ -54,7 +54,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="override vertex count (debug)")
+    ap.add_argument("--n", "--vertices", dest="n", type=int, default=None,
+                    help="override the per-GPU vertex count")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
                     help="single-GPU record runs of the other BASELINE configs")
     ap.add_argument("--cpu-columns", type=int, default=4)
