@@ -6,15 +6,25 @@
 //
 //   * a persistent CTA owns row tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //   * warp 0 is a producer: for each tile it issues 1-D TMA bulk copies
-//     (cp.async.bulk ... mbarrier::complete_tx) of the tile's CSR slab
+//     (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first) of the tile's CSR slab
 //     (indptr / indices / values) and of the tile's x_old and r rows into a
-//     ring of `stages` shared-memory stages, several tiles ahead;
+//     ring of `stages` shared-memory stages; the tile's first/last CSR offsets are
+//     fetched one tile ahead so that their latency is off the critical path;
 //   * the consumer warps wait on the stage's "full" mbarrier, read the CSR
-//     entries from shared memory (broadcast, no shuffles), gather x_cur rows with
-//     coalesced 16-byte loads through L1/L2 (the only traffic left on that path,
-//     so L1 holds nothing but x_cur), accumulate in registers in stored CSR
+//     entries from shared memory four at a time (LDS.128, no shuffles), gather x_cur
+//     rows with coalesced 16-byte loads through L1/L2 (the only traffic left on that
+//     path, so L1 holds nothing but x_cur), accumulate in registers in stored CSR
 //     order, apply the three-term recurrence and the coefficient AXPYs and store
 //     x_new / r with streaming 16-byte stores; then release the stage ("empty").
+//
+// Two optional roles of the same kernel:
+//   * add_source (Clenshaw form): the r tiles are read-only source blocks,
+//     x_new += sum_i ck_i s_i, nothing is written to r  (single-filter Clenshaw and
+//     the fused synthesis of Filter.filter);
+//   * halo fusion (vertex-partitioned path): wait for the neighbours' flags in the
+//     prologue, store boundary rows of x_new into the neighbours' halo rows from
+//     the epilogue (peer stores over NVLink), publish the step when the last
+//     boundary tile is done  (gsp_halo_fusion in the header).
 //
 // Lane mapping: G = nsig/4 lanes own one row (a float4 packet each), 32/G rows
 // per warp in flight.  A tile's slab must fit `slab_cap` entries: the caller

@@ -87,3 +87,31 @@ def test_jackson_coefficients(golden):
     assert bounds == [1.0, 4.0]                      # the caller's list is left alone
     with pytest.raises(ValueError):
         filters.compute_jackson_cheby_coeff([1.0, 20.0], [0.0, 13.9], 10)
+
+
+def test_ritz_check_on_a_host_lanczos():
+    """The stopping rule shared by Graph.estimate_lmax and the distributed estimate, driven
+    by a NumPy Lanczos on a small Laplacian: stops, and the estimate brackets the truth."""
+    from scipy import sparse
+    from pygsp_b200.graphs.graph import ritz_check
+    rng = np.random.default_rng(0)
+    A = sparse.random(400, 400, 0.03, random_state=0, format="csr")
+    A = A + A.T
+    L = (sparse.diags(np.asarray(A.sum(axis=1)).ravel()) - A).tocsr()
+    lam = np.linalg.eigvalsh(L.toarray())[-1]
+    v = rng.standard_normal(400); v /= np.linalg.norm(v)
+    v_prev, beta_prev, alphas, betas = None, 0.0, [], []
+    for j in range(200):
+        w = L @ v
+        a = float(w @ v); w = w - a * v - (beta_prev * v_prev if v_prev is not None else 0)
+        b = float(np.linalg.norm(w)); alphas.append(a); betas.append(b)
+        if (j + 1) >= 10 and (j + 1 - 10) % 5 == 0:
+            theta, m, stop, ref_rule = ritz_check(np.array(alphas), np.array(betas), 5e-3, False, j + 1 >= 60)
+            if stop:
+                break
+        v_prev, beta_prev, v = v, b, w / b
+    assert stop and ref_rule and j + 1 <= 60
+    assert lam * (1 - 1e-4) <= theta <= lam * (1 + 1e-12)
+    # an exactly invariant start vector: beta_0 = 0 stops at once with the exact eigenvalue
+    theta, m, stop, _ = ritz_check(np.array([3.0]), np.array([0.0]), 5e-3, False, False)
+    assert stop and m == 1 and theta == 3.0
