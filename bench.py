@@ -298,8 +298,8 @@ def build_single(gsp, wl, rank):
         G = gsp.graphs.Grid2d(side, side)             # stencil written on the device
     elif wl["graph"] == "sbm":
         G = gsp.graphs.StochasticBlockModel(wl["N"], k=wl["k"], p=5e-6, q=5e-7, seed=wl["seed"])
-    else:
-        G = gsp.graphs.Graph(host_graph(wl["N"], wl["k"], wl["seed"]))
+    else:                                             # grid-hash k-NN + symmetrisation on the device
+        G = gsp.graphs.Sensor(wl["N"], k=wl["k"], seed=wl["seed"], order="morton")
     G.estimate_lmax()
     return G
 

@@ -174,11 +174,13 @@ class NNGraph(Graph):
     ``w_ij = exp(-d_ij^2 / sigma)`` for the k nearest neighbours j of i, sigma =
     mean neighbour distance, then ``W <- (W + W^T)/2`` -- the 'knn' branch of
     pygsp/graphs/nngraphs/nngraph.py:147-226,289-297 with its default
-    ``center`` / ``rescale`` preprocessing (:127-136).
+    ``center`` / ``rescale`` preprocessing (:127-136).  ``backend='device'`` (default for
+    2-D / 3-D clouds, k <= 32) searches and assembles in HBM (csrc/generate.cu);
+    ``backend='host'`` uses scipy's cKDTree.  Both give the same adjacency.
     """
 
     def __init__(self, Xin, k=10, sigma=None, center=True, rescale=True, order=None,
-                 backend="host", **kwargs):
+                 backend=None, **kwargs):
         Xin = np.asarray(Xin, dtype=np.float64)
         N, d = Xin.shape
         if k >= N:
@@ -192,6 +194,8 @@ class NNGraph(Graph):
             X = X[morton_order(X)]
         elif order is not None:
             X = X[np.asarray(order)]
+        if backend is None:     # the device search covers 2-D / 3-D clouds and k <= 32
+            backend = "device" if (d in (2, 3) and k <= 32) else "host"
         if backend == "device":                     # grid-hash k-NN + symmetrisation in HBM
             W, sigma = knn_adjacency_device(X, k, sigma, kwargs.get("dtype"), kwargs.get("device"))
             self.k, self.sigma = k, sigma
@@ -216,7 +220,7 @@ class Sensor(NNGraph):
     along a Z-curve (an isomorphic graph with gather-friendly numbering).
     """
 
-    def __init__(self, N=64, k=6, seed=None, order=None, backend="host", **kwargs):
+    def __init__(self, N=64, k=6, seed=None, order=None, backend=None, **kwargs):
         self.seed = seed
         kwargs["backend"] = backend
         coords = np.random.default_rng(seed).uniform(0, 1, (N, 2))
