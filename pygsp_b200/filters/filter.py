@@ -27,15 +27,14 @@ class Filter:
 
     def __init__(self, G, kernels):
         self.G = G
-        try:
-            iter(kernels)
-        except TypeError:
-            kernels = [kernels]
-        self._kernels = kernels
-        self.n_features_in, self.n_features_out = (1, len(kernels))
-        self.shape = (self.n_features_out, self.n_features_in)
-        self.n_filters = self.n_features_in * self.n_features_out
-        self.Nf = self.n_filters
+        single = callable(kernels) and not hasattr(kernels, "__iter__")
+        self._kernels = [kernels] if single else kernels
+        n_out = len(self._kernels)
+        # one input feature, one output feature per kernel (an "analysis" bank)
+        self.n_features_in = 1
+        self.n_features_out = n_out
+        self.shape = (n_out, 1)
+        self.Nf = self.n_filters = n_out
         # synthesis as ONE backward recurrence (K SpMMs) instead of the reference's Nf
         # forward recurrences (Nf * K SpMMs); same value, different rounding.  Set to
         # False to reproduce the reference's operation order.
@@ -45,10 +44,9 @@ class Filter:
         return dict()
 
     def __repr__(self):
-        attrs = {"in": self.n_features_in, "out": self.n_features_out}
-        attrs.update(self._get_extra_repr())
-        return "{}({})".format(type(self).__name__,
-                               ", ".join("{}={}".format(k, v) for k, v in attrs.items()))
+        fields = [("in", self.n_features_in), ("out", self.n_features_out)]
+        fields += list(self._get_extra_repr().items())
+        return "{}({})".format(type(self).__name__, ", ".join("%s=%s" % kv for kv in fields))
 
     def __len__(self):
         return self.n_filters
@@ -71,11 +69,11 @@ class Filter:
 
     def evaluate(self, x):
         r"""Frequency response of every kernel at ``x``: shape (Nf, *x.shape)."""
-        x = np.asanyarray(x)
-        y = np.empty([self.Nf] + list(x.shape))
-        for i, kernel in enumerate(self._kernels):
-            y[i] = kernel(x)
-        return y
+        freqs = np.asanyarray(x)
+        response = np.empty((self.Nf,) + freqs.shape)
+        for row, g in zip(response, self._kernels):
+            row[...] = g(freqs)
+        return response
 
     def filter(self, s, method="chebyshev", order=30):
         r"""Filter signals (analysis or synthesis) -- filter.py:146-328.
@@ -150,6 +148,6 @@ class Filter:
 
     def localize(self, i, **kwargs):
         r"""Kernels localised at vertex ``i``: sqrt(N) g(L) delta_i (filter.py:350-391)."""
-        s = np.zeros(self.G.N)
-        s[i] = 1
-        return np.sqrt(self.G.N) * self.filter(s, **kwargs)
+        delta = np.zeros(self.G.N)
+        delta[i] = 1
+        return self.filter(delta, **kwargs) * np.sqrt(self.G.N)
