@@ -31,7 +31,8 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
-                         int64_t* rows_done, cudaStream_t st, bool add_source = false);
+                         int64_t* rows_done, cudaStream_t st, bool add_source = false,
+                         bool reverse = false);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -262,7 +263,7 @@ static int cheby_step_planned(const gsp_tile_plan* plan, int64_t nnz, bool first
                               const T* vals, const T* x_cur, const T* x_old, T* x_new, T* r,
                               int64_t r_rows, int nsig, int nscales, const double* ck,
                               const double* c0, double alpha, double beta, double gamma,
-                              cudaStream_t st, bool add_source = false) {
+                              cudaStream_t st, bool add_source = false, bool reverse = false) {
   return cheby_step<T>(first, rb, re, indptr, indices, vals, x_cur, x_old, x_new, r, r_rows, nsig,
                        nscales, ck, c0, alpha, beta, gamma, st, add_source);
 }
@@ -275,7 +276,7 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
                               const float* vals, const float* x_cur, const float* x_old,
                               float* x_new, float* r, int64_t r_rows, int nsig, int nscales,
                               const double* ck, const double* c0, double alpha, double beta,
-                              double gamma, cudaStream_t st, bool add_source) {
+                              double gamma, cudaStream_t st, bool add_source, bool reverse) {
   const bool tiled = plan && plan->rows_per_tile > 0 && rb % 4 == 0 && nscales <= kMaxScales &&
                      aligned16(indptr) && aligned16(indices) && aligned16(vals) &&
                      aligned16(x_cur) && aligned16(x_new) && aligned16(r) &&
@@ -284,7 +285,7 @@ int cheby_step_planned<float>(const gsp_tile_plan* plan, int64_t nnz, bool first
   if (tiled) {
     int rc = cheby_step_tiled_f32(first, rb, re, nnz, indptr, indices, vals, x_cur, x_old, x_new, r,
                                   r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *plan, nullptr,
-                                  &done, st, add_source);
+                                  &done, st, add_source, reverse);
     if (rc != GSP_OK) return rc;
   }
   return cheby_step<float>(first, rb + done, re, indptr, indices, vals, x_cur, x_old, x_new, r,
@@ -320,8 +321,11 @@ int cheby_op(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indic
       // T_k = (4/lmax) L T_{k-1} - 2 T_{k-1} - T_{k-2}, written over T_{k-2}
       // (row-local) except for k == 2 where T_0 is the caller's input.
       T* dst = (k == 2) ? buf[1] : const_cast<T*>(t_old);
+      // odd steps walk the tiles backwards: the lines of T_{k-1} and r that the previous
+      // step wrote last are still in L2 and are the first ones this step reads
       rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, t_cur, t_old, dst,
-                                 r, n, nsig, nscales, ck, c0, 4.0 / lmax, -2.0, -1.0, st);
+                                 r, n, nsig, nscales, ck, c0, 4.0 / lmax, -2.0, -1.0, st, false,
+                                 (k & 1) == 0);
       t_old = t_cur;
       t_cur = dst;
     }
@@ -414,7 +418,8 @@ int cheby_clenshaw(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t*
     }
     T* dst = last ? out : (b_old ? const_cast<T*>(b_old) : buf[1]);
     int rc = cheby_step_planned<T>(plan, nnz, false, 0, n, indptr, indices, vals, b_cur, old, dst,
-                                   xs, n, nsig, nsrc, ck, zero, alpha, beta, gamma, st, true);
+                                   xs, n, nsig, nsrc, ck, zero, alpha, beta, gamma, st, true,
+                               (k & 1) == 0);
     if (rc != GSP_OK) return rc;
     b_old = b_cur;
     b_cur = dst;

@@ -59,6 +59,8 @@ struct TileArgs {
   float ck[kTiledMaxScales];
   gsp_halo_fusion halo;   // all zero when the step does not exchange a halo
   int l2_hint;            // evict-first hint on the streamed TMA copies
+  int keep_writes;        // plain instead of evict-first stores for x_new / r
+  int reverse;            // walk the tiles from the last to the first (see cheby_op)
   int stage_xcur;         // stage the tile's own x_cur rows (XS variant)
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
 };
@@ -121,6 +123,11 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
 }
 __device__ __forceinline__ void stcs_f4(float* p, const float4& v) {
   __stcs(reinterpret_cast<float4*>(p), v);
+}
+// x_new / r: streaming (evict-first) stores, or plain ones when the next step walks the
+// tiles in the opposite direction and re-reads the lines this step wrote last
+__device__ __forceinline__ void store_f4(float* p, const float4& v, bool keep) {
+  if (keep) *reinterpret_cast<float4*>(p) = v; else stcs_f4(p, v);
 }
 
 // shared-memory carve-up, identical on host and device
@@ -192,16 +199,19 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     // DRAM latency is not in series with the wait for a free slot
     int nbegin = 0, nend = 0;
     if (int64_t(blockIdx.x) < a.n_tiles) {
-      const int64_t rn = a.row_begin + int64_t(blockIdx.x) * R;
+      const int64_t first_tile = a.reverse ? a.n_tiles - 1 - int64_t(blockIdx.x) : int64_t(blockIdx.x);
+      const int64_t rn = a.row_begin + first_tile * R;
       nbegin = __ldg(a.indptr + rn);
       nend = __ldg(a.indptr + rn + R);
     }
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (int64_t slot = blockIdx.x; slot < a.n_tiles; slot += gridDim.x, ++it) {
+      const int64_t tile = a.reverse ? a.n_tiles - 1 - slot : slot;
       const int s = it % S;
       const uint32_t round = uint32_t(it / S);
       const int begin = nbegin, end = nend;
-      if (tile + gridDim.x < a.n_tiles) {
-        const int64_t rn = a.row_begin + (tile + gridDim.x) * R;
+      if (slot + gridDim.x < a.n_tiles) {
+        const int64_t nslot = slot + gridDim.x;
+        const int64_t rn = a.row_begin + (a.reverse ? a.n_tiles - 1 - nslot : nslot) * R;
         nbegin = __ldg(a.indptr + rn);
         nend = __ldg(a.indptr + rn + R);
       }
@@ -266,8 +276,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
   const int nscales = NSC >= 0 ? NSC : a.nscales;
   const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
+  const bool keep_writes = a.keep_writes != 0;
   int it = 0;
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+  for (int64_t slot = blockIdx.x; slot < a.n_tiles; slot += gridDim.x, ++it) {
+    const int64_t tile = a.reverse ? a.n_tiles - 1 - slot : slot;
     const int s = it % S;
     const uint32_t round = uint32_t(it / S);
     mbar_wait(full + s, round & 1u);
@@ -369,7 +381,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           xn.w = fmaf(w, sv.w, xn.w);
         }
       }
-      stcs_f4(xn_tile + off, xn);
+      store_f4(xn_tile + off, xn, keep_writes);
       if (push_tile) {
         // fused halo push: this row's new value goes straight into the halo rows of
         // the neighbours that reference it (peer stores over NVLink)
@@ -401,7 +413,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           rv.z = fmaf(ck, xn.z, rv.z);
           rv.w = fmaf(ck, xn.w, rv.w);
         }
-        stcs_f4(r_tile + i * r_stride + off, rv);
+        store_f4(r_tile + i * r_stride + off, rv, keep_writes);
       }
     }
     if (push_tile) {
@@ -537,8 +549,10 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
-                         int64_t* rows_done, cudaStream_t st, bool add_source) {
+                         int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse) {
   TileArgs a;
+  a.keep_writes = env_int("GSPB200_TILE_REV", 1);
+  a.reverse = (reverse && a.keep_writes && !halo) ? 1 : 0;
   a.add_source = add_source ? 1 : 0;
   a.l2_hint = env_int("GSPB200_TILE_HINT", 1);
   a.stage_xcur = env_int("GSPB200_TILE_XS", 0);
