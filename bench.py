@@ -4,8 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 metric  = cheby_op filtered-vertices/sec = N * Nsig * order / t
-workload (N=1): BASELINE configs[1] -- Sensor-type 2-D k-NN graph, N = 1e6, k = 10,
-          seed 0 (Morton-numbered), 64 float32 signals, Heat(scale=50), order 30.
+workload, 1 GPU : BASELINE configs[1] -- Sensor-type 2-D k-NN graph, N = 1e6, k = 10,
+          seed 0 (Morton-numbered), 64 float32 signals, Heat(scale=50), order 30; the same
+          line carries `targets`: short runs of the north-star target (10M-vertex k-NN) and of
+          configs[2] (10M-vertex grid, 6-filter MexicanHat, order 50) with their parity.
+workload, N > 1 : STRONG scaling of the north-star target -- ONE 10M-vertex k-NN graph
+          (the 1-GPU `targets.knn10m` graph) 1-D partitioned over the N ranks, halo exchange
+          per recurrence step over NVLink peer memory; every line carries `parity_rel_err`
+          (partitioned result vs the single-GPU engine on the whole graph, every rank) and the
+          one-GPU time of the same graph measured in the same run.  --scaling weak = 1e6
+          vertices per GPU (strips of one k-NN graph).
 A "step" is one complete cheby_op call (order fused recurrence kernels).
 
 value   : CUDA-event time of K calls with graph + signals resident in HBM.
@@ -45,6 +53,8 @@ WORKLOADS = {
                     nscales=6),
     "config4": dict(name="sbm_N1e7_k8_p5e-6_q5e-7_heat50_order30_nsig32", N=10_000_000, k=8,
                     seed=0, nsig=32, order=30, scale=50.0, graph="sbm", bank="heat", nscales=1),
+    "config5": dict(name="knn3d_N5e7_k16_seed0_morton_heat50_order40_nsig128", N=50_000_000, k=16,
+                    seed=0, nsig=128, order=40, scale=50.0, graph="knn3d", bank="heat", nscales=1),
 }
 
 
@@ -56,8 +66,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--vertices", dest="n", type=int, default=None,
                     help="override the per-GPU vertex count")
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
-                    help="single-GPU record runs of the other BASELINE configs")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: config2 on one GPU, knn10m (strong scaling) on N > 1")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: one fixed graph split over the ranks (default) or 1e6 vertices per GPU")
+    ap.add_argument("--no-targets", action="store_true",
+                    help="skip the short runs of the 10M k-NN target and config 3 in the 1-GPU line")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-columns", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -80,11 +95,46 @@ def host_graph(n, k, seed):
     return W
 
 
-def algorithmic_bytes(n, nnz, nsig, nscales, order, itemsize=4):
-    """compulsory traffic of the reference algorithm."""
-    first = (4 + itemsize) * nnz + 4 * (n + 1) + itemsize * n * nsig * (2 + nscales)
-    step = (4 + itemsize) * nnz + 4 * (n + 1) + itemsize * n * nsig * (3 + 2 * nscales)
+def algorithmic_bytes(n, nnz, nsig, nscales, order, itemsize=4, clenshaw=False):
+    """Compulsory HBM traffic of one call: (first step, dominant step, whole call).
+
+    Forward recurrence = the reference's algorithm, SURVEY.md 8(d): CSR once, T_{k-1} once,
+    T_{k-2} read, T_k written, every r block read + written: 3 + 2 Nscales passes over the
+    signal block per step (2 + Nscales for the first).  Clenshaw form (single filter, the
+    engine's default): no accumulator block -- b_{k+1} read, b_{k+2} read, source read, b_k
+    written = 4 passes (first step 2, second 3: b_K = c_K x is folded into the source)."""
+    csr = (4 + itemsize) * nnz + 4 * (n + 1)
+    vec = itemsize * n * nsig
+    if clenshaw and nscales == 1 and order >= 2:
+        first, step = csr + 2 * vec, csr + 4 * vec
+        return first, step, order * csr + vec * (2 + 3 + 4 * (order - 2))
+    first = csr + vec * (2 + nscales)
+    step = csr + vec * (3 + 2 * nscales)
     return first, step, first + (order - 1) * step
+
+
+def config_dict(wl, world, scaling):
+    """The `config` object of a bench line: the same keys and values on both arms."""
+    n_global = wl["N"] * (world if scaling == "weak" else 1)
+    return {"workload": wl["name"], "N_global": n_global, "N_per_gpu": n_global // world,
+            "k": wl["k"], "nsig": wl["nsig"], "order": wl["order"], "nscales": wl["nscales"],
+            "scaling": scaling if world > 1 else "single GPU",
+            "partition": "single GPU" if world == 1 else
+                         "1-D vertex partition, %d contiguous row blocks, halo exchange per "
+                         "recurrence step" % world,
+            "l2_policy": "inputs_exceed_l2 (the state blocks of a call are >= 0.5 GB per GPU, "
+                         "L2 is 126 MB)"}
+
+
+def pick_workload(args, world):
+    """(workload dict, scaling).  One GPU: configs[1].  N > 1: strong scaling of the 10M-vertex
+    k-NN target (weak: 1e6-vertex strips); config4 / config5 are strong by definition."""
+    name = args.workload or ("config2" if (world == 1 or args.scaling == "weak") else "knn10m")
+    wl = dict(WORKLOADS[name])
+    if args.n:
+        wl["N"] = args.n
+    scaling = "weak" if (world > 1 and name == "config2") else "strong"
+    return name, wl, scaling
 
 
 class ClockSampler:
@@ -167,15 +217,18 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full`
+    capture of THIS workload on one GPU (profiles/roofline_traffic.json, keyed by workload);
+    None when no capture exists (multi-GPU runs, other workloads)."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(path):
-        try:
-            return float(json.load(open(path))["dram_bytes_per_launch"])
-        except Exception:
-            return None
-    return None
+    if workload is None or not os.path.exists(path):
+        return None
+    try:
+        entry = json.load(open(path)).get(workload)
+        return float(entry["dram_bytes_per_launch"]) if entry else None
+    except Exception:
+        return None
 
 
 # -------------------------------------------------------------- CPU reference
@@ -258,32 +311,37 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import pygsp_oracle as orc
-    wl = dict(WORKLOAD)
-    if args.n:
-        wl["N"] = args.n
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    name, wl, scaling = pick_workload(args, world)
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
-    W = host_graph(wl["N"], wl["k"], wl["seed"])
+    # The CPU path is timed on the 1e6-vertex instance of the workload's generator (same k,
+    # seed, weights, order, filter): that IS configs[1]; for the 10M-vertex target it is the
+    # 1/10-scale instance SURVEY.md 8(d) prescribes for CPU timing -- the metric is a rate
+    # (vertex*signal*order per second), so no extrapolation enters the value.
+    n_cpu = min(wl["N"], 1_000_000)
+    W = host_graph(n_cpu, wl["k"], wl["seed"])
     lmax = orc.upper_bound(W)                  # estimate_lmax(method="bounds"): deterministic
     ncols = min(wl["nsig"], procs)              # bounded sample: one signal column per process
-    x = np.random.default_rng(0).standard_normal((wl["N"], ncols))
+    x = np.random.default_rng(0).standard_normal((n_cpu, ncols))
     ref = CpuReference(W, lmax, wl["scale"], wl["order"], x, procs)
     for _ in range(min(args.warmup, 1)):
         ref.time_once()
     times = [ref.time_once() for _ in range(args.steps)]
     ref.close()
     t = float(np.sum(times))
-    value = wl["N"] * ncols * wl["order"] * args.steps / t
+    value = n_cpu * ncols * wl["order"] * args.steps / t
     what = ("unmodified PyGSP 0.6.1 from baseline/_ref, Heat(G, 50).filter(x, order=30)"
             if ref.kind == "reference" else "oracle port of approximations.cheby_op")
-    sample = "%d of %d signal columns per step (one per process), full graph, full order; %s" % (
-        ncols, wl["nsig"], what)
+    sample = "%d of %d signal columns per step (one per process), %s, full order; %s" % (
+        ncols, wl["nsig"], "full graph" if n_cpu == wl["N"] else
+        "the N=%d instance of the same generator (1/%d scale)" % (n_cpu, wl["N"] // n_cpu), what)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": wl["name"], **{k: wl[k] for k in
-                                        ("N", "k", "nsig", "order")}, "nnz_W": int(W.nnz)},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(wl, world, scaling),
+        "graph": {"N_timed": n_cpu, "nnz_W": int(W.nnz), "lmax": lmax},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.procs, "kind": ref.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -291,8 +349,8 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------- our arm
-def build_single(gsp, wl, rank):
-    """N = 1: Graph API end to end (device Laplacian, device Lanczos lmax)."""
+def build_graph(gsp, wl):
+    """The workload's graph through the Graph API: adjacency, Laplacian and lmax on the device."""
     if wl["graph"] == "grid2d":
         side = int(round(wl["N"] ** 0.5))
         G = gsp.graphs.Grid2d(side, side)             # stencil written on the device
@@ -302,6 +360,80 @@ def build_single(gsp, wl, rank):
         G = gsp.graphs.Sensor(wl["N"], k=wl["k"], seed=wl["seed"], order="morton")
     G.estimate_lmax()
     return G
+
+
+def make_bank(gsp, G, wl):
+    bank = (gsp.filters.MexicanHat(G, Nf=wl["nscales"]) if wl["bank"] == "mexicanhat"
+            else gsp.filters.Heat(G, scale=wl["scale"]))
+    c = np.atleast_2d(gsp.filters.compute_cheby_coeff(bank, m=wl["order"]))
+    return bank, c
+
+
+def device_op(apx, L, lmax, c):
+    """The device-to-device operator the public API runs: Clenshaw form for one filter."""
+    if c.shape[0] == 1:
+        return lambda xx: apx.cheby_clenshaw_device(L, lmax, c, xx)[None]
+    return lambda xx: apx.cheby_op_device(L, lmax, c, xx)
+
+
+def csr_row_block(L, lo, hi):
+    """Rows [lo, hi) of a DeviceCSR as a host scipy matrix with global column ids."""
+    from scipy import sparse
+    ptr = L.indptr[lo:hi + 1].cpu().numpy().astype(np.int64)
+    a, b = int(ptr[0]), int(ptr[-1])
+    return sparse.csr_matrix((L.data[a:b].cpu().numpy(), L.indices[a:b].cpu().numpy(), ptr - a),
+                             shape=(hi - lo, L.shape[1]))
+
+
+def time_calls(torch, fn, x, steps, warm):
+    """ms per call: CUDA events on the current stream around `steps` calls, after `warm` calls."""
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warm):
+        fn(x)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(steps):
+        fn(x)
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / steps
+
+
+def oracle_parity(L, lmax, c, x_col, got):
+    """max|got - ref| / max|ref| of one signal column against the float64 oracle (CPU)."""
+    from oracle import pygsp_oracle as orc
+    ref = orc.cheby_op(L.to_scipy().astype(np.float64), lmax, c, x_col.double().cpu().numpy())
+    ref = ref.reshape(c.shape[0], -1)
+    got = got.double().cpu().numpy().reshape(c.shape[0], -1)
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+def run_target(gsp, apx, torch, name, peak):
+    """Short run of another BASELINE workload on this GPU: 3 timed calls after 1 warm-up,
+    roofline fraction, one signal column checked against the float64 oracle."""
+    wl = dict(WORKLOADS[name])
+    t0 = time.perf_counter()
+    G = build_graph(gsp, wl)
+    bank, c = make_bank(gsp, G, wl)
+    t_build = time.perf_counter() - t0
+    n, nsig, order = G.N, wl["nsig"], wl["order"]
+    x = torch.randn(n, nsig, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    op = device_op(apx, G.L, G.lmax, c)
+    ms = time_calls(torch, op, x, 3, 1)
+    clen = c.shape[0] == 1
+    _, b_step, b_call = algorithmic_bytes(n, G.L.nnz, nsig, wl["nscales"], order, clenshaw=clen)
+    col = x[:, :1].contiguous()
+    parity = oracle_parity(G.L, G.lmax, c, col, device_op(apx, G.L, G.lmax, c)(col))
+    out = {"workload": wl["name"], "N": n, "nnz_L": G.L.nnz, "nsig": nsig, "nscales": wl["nscales"],
+           "order": order, "steps": 3, "warmup": 1, "ms_per_step": ms,
+           "value": n * nsig * order / (ms / 1e3), "value_bank": n * nsig * order * wl["nscales"] / (ms / 1e3),
+           "unit": UNIT, "form": "clenshaw" if clen else "forward",
+           "roofline_frac": b_call / (ms / 1e3) / 1e9 / peak, "achieved_GBps": b_call / (ms / 1e3) / 1e9,
+           "algorithmic_bytes_per_call": b_call, "parity_rel_err_one_column_vs_oracle": parity,
+           "lmax": G.lmax, "build_s": t_build}
+    del G, x, op, col
+    torch.cuda.empty_cache()
+    return out
 
 
 def build_partitioned_sbm(gsp, wl, rank, world, torch, dist):
@@ -316,14 +448,13 @@ def build_partitioned_sbm(gsp, wl, rank, world, torch, dist):
     L_rows, dw = laplacian_rows(W[lo:hi], lo)
     del W
     plan = gd.HaloPlan(L_rows, bounds, rank)
-    op = gd.PartitionedCheby(plan, dtype=torch.float32,
-                             exchange=os.environ.get("GSPB200_EXCHANGE"))
+    op = gd.PartitionedCheby(plan, dtype=torch.float32, exchange=os.environ.get("GSPB200_EXCHANGE"))
     op.fuse_halo = os.environ.get("GSPB200_FUSE_HALO", "1") != "0"
     return op, op.estimate_lmax(), int(L_rows.nnz)
 
 
-def build_partitioned(gsp, wl, rank, world, torch, dist):
-    """N > 1 (weak scaling): strip q = rank q's 1e6-vertex row block of ONE k-NN graph on
+def build_partitioned_strips(gsp, wl, rank, world, torch, dist):
+    """Weak scaling: strip q = rank q's 1e6-vertex row block of ONE k-NN graph on
     [0, P) x [0, 1); halo exchange per recurrence step."""
     from pygsp_b200 import distributed as gd
     from pygsp_b200.graphs.generators import SensorStrips, laplacian_rows
@@ -340,6 +471,19 @@ def build_partitioned(gsp, wl, rank, world, torch, dist):
     return op, op.estimate_lmax(), int(L_rows.nnz)       # distributed Lanczos, as on one GPU
 
 
+def build_partitioned_from_graph(G, rank, world, torch):
+    """Strong scaling: every rank holds the SAME graph (built through the Graph API with the
+    same seed, exactly the one-GPU graph) and keeps the row block [N p/P, N (p+1)/P) of its
+    Laplacian for the partitioned operator; the full copy stays for the in-run parity leg."""
+    from pygsp_b200 import distributed as gd
+    bounds = gd.even_bounds(G.N, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    plan = gd.HaloPlan(csr_row_block(G.L, lo, hi), bounds, rank)
+    op = gd.PartitionedCheby(plan, dtype=torch.float32, exchange=os.environ.get("GSPB200_EXCHANGE"))
+    op.fuse_halo = os.environ.get("GSPB200_FUSE_HALO", "1") != "0"
+    return op, (lo, hi)
+
+
 def run_ours(args):
     import ctypes
     import torch
@@ -351,60 +495,76 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_cpus = gsp.utils.bind_to_gpu_numa(local)      # pinned staging memory on the GPU's socket
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    wl = dict(WORKLOADS[args.workload])
-    if args.n:
-        wl["N"] = args.n
-    n, nsig, order = wl["N"], wl["nsig"], wl["order"]
-    if world > 1 and args.workload not in ("config2", "config4"):
-        raise SystemExit("--workload %s is a single-GPU option" % args.workload)
-    strong = world > 1 and args.workload == "config4"      # one fixed graph split over the ranks
+    name, wl, scaling = pick_workload(args, world)
+    nsig, order = wl["nsig"], wl["order"]
+    if world > 1 and name == "config3":
+        raise SystemExit("--workload config3 is a single-GPU option")
     lib = gsp._native.lib()
     lib.gsp_launch_count.restype = ctypes.c_uint64
+    peak, peak_src = measured_peak()
 
     clocks = ClockSampler(local)
     clocks.__enter__()                       # running long before the timed region
-
-    # ---- build the workload (untimed)
-    if world == 1:
-        G = build_single(gsp, wl, rank)
-        n = wl["N"] = G.N
-        L, lmax, nnz = G.L, G.lmax, G.L.nnz
-        heat = (gsp.filters.MexicanHat(G, Nf=wl["nscales"]) if wl["bank"] == "mexicanhat"
-                else gsp.filters.Heat(G, scale=wl["scale"]))
-        c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
-        run_dev = lambda xx: apx.cheby_op_device(L, lmax, c, xx)
-        run_host = lambda xh: heat.filter(xh, order=order)
-        halo = None
-    else:
-        if strong:
-            op, lmax, nnz = build_partitioned_sbm(gsp, wl, rank, world, torch, dist)
-            n = op.plan.n_local
-        else:
-            op, lmax, nnz = build_partitioned(gsp, wl, rank, world, torch, dist)
-
-        class _G:           # coefficients need only lmax (approximations.py:40)
-            pass
-        g = _G(); g.lmax = lmax; g.N = n
-        heat = gsp.filters.Heat(g, scale=wl["scale"])
-        c = np.atleast_2d(gsp.filters.compute_cheby_coeff(heat, m=order))
-        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=True)
-
-        def run_host(xh):
-            y = op.cheby_op(lmax, c, xh.to("cuda", non_blocking=True))[0]
-            out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
-            out.copy_(y)
-            return out
-        halo = {"rows_received_per_rank": op.plan.n_halo, "boundary_rows": op.plan.n_true_boundary}
-    gen = torch.Generator(device="cuda").manual_seed(rank)
-    x = torch.randn(n, nsig, device="cuda", generator=gen)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- build the workload (untimed)
+    G = op = None
+    lo = 0
+    t_build0 = time.perf_counter()
+    if world == 1 or (scaling == "strong" and wl["graph"] in ("sensor", "grid2d")):
+        G = build_graph(gsp, wl)                     # the one-GPU graph, on every rank
+        n_global = wl["N"] = G.N
+        lmax, nnz_global = G.lmax, G.L.nnz
+        bank, c = make_bank(gsp, G, wl)
+        if world > 1:
+            op, (lo, hi) = build_partitioned_from_graph(G, rank, world, torch)
+            n, nnz = hi - lo, int(op.plan.nnz)
+        else:
+            n, nnz = G.N, G.L.nnz
+    else:
+        if wl["graph"] == "sbm":
+            op, lmax, nnz = build_partitioned_sbm(gsp, wl, rank, world, torch, dist)
+        else:
+            op, lmax, nnz = build_partitioned_strips(gsp, wl, rank, world, torch, dist)
+        n = op.plan.n_local
+        n_global = op.plan.n_global
+        lo = int(op.plan.bounds[rank])
+
+        class _G:           # coefficients need only lmax (approximations.py:40)
+            pass
+        g = _G(); g.lmax = lmax; g.N = n
+        bank = gsp.filters.Heat(g, scale=wl["scale"])
+        c = np.atleast_2d(gsp.filters.compute_cheby_coeff(bank, m=order))
+        t = torch.tensor([nnz], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        nnz_global = int(t.item())
+    t_build = time.perf_counter() - t_build0
+    clen = c.shape[0] == 1                           # the engine's default form for one filter
+    # signals: one seeded global block, every rank takes its rows (strong scaling keeps the
+    # whole block for the parity leg against the one-GPU engine)
+    gen = torch.Generator(device="cuda").manual_seed(0 if G is not None else rank)
+    x_full = torch.randn(n_global if G is not None else n, nsig, device="cuda", generator=gen)
+    x = x_full[lo:lo + n].contiguous() if (G is not None and world > 1) else x_full
+    if world == 1:
+        run_dev = device_op(apx, G.L, lmax, c)
+        run_host = lambda xh: bank.filter(xh, order=order)
+    else:
+        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=False)
+        run_host = lambda xh: op.filter_pinned(lmax, c, xh)[0]
 
     # ---- device-resident throughput ("value")
     warm = max(args.warmup, 3)
@@ -416,22 +576,19 @@ def run_ours(args):
     t_region0 = time.time()
     start.record()
     for _ in range(args.steps):
-        run_dev(x)
+        y_dev = run_dev(x)
     stop.record()
     barrier()
     t_region1 = time.time()
     launches = int(lib.gsp_launch_count() - launches0)
     time.sleep(0.1)                                      # let the sampler emit its last lines
     clocks.__exit__()
-    t_all = torch.tensor([start.elapsed_time(stop) / 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    t_dev = float(t_all.item())
-    value = world * n * nsig * order * args.steps / t_dev
+    t_dev = allmax(start.elapsed_time(stop) / 1e3)
+    value = n_global * nsig * order * args.steps / t_dev
 
     # ---- end to end through the public API with host buffers
-    e2e_value, t_e2e = None, float("nan")
-    if args.workload == "config2":             # the record runs of the big configs skip it
+    e2e = None
+    if not args.no_e2e and wl["nscales"] == 1 and n * nsig * 4 <= (4 << 30):
         xh = torch.empty((n, nsig), dtype=torch.float32).pin_memory()
         xh.copy_(x)
         for _ in range(2):
@@ -439,32 +596,71 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            yh = run_host(xh)
+            yh = run_host(xh)                 # returns a complete host tensor (synchronises)
         torch.cuda.synchronize()
-        t_all = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        t_e2e = float(t_all.item())
-        e2e_value = world * n * nsig * order * args.steps / t_e2e
+        t_e2e = allmax(time.perf_counter() - t0)
         assert tuple(yh.shape)[:2] == (n, nsig) and not yh.is_cuda
+        e2e_err = float((yh.to("cuda") - y_dev[0]).abs().max() / y_dev[0].abs().max())
+        from pygsp_b200.filters import pipeline
+        wchunk = pipeline.chunk_width(n_global // world, nsig, 4)
+        e2e = {"value": n_global * nsig * order * args.steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": 4 * n_global * nsig,
+               "d2h_bytes_per_step": 4 * n_global * nsig * wl["nscales"],
+               "ms_per_step": 1e3 * t_e2e / args.steps,
+               "api": ("%s.filter(pinned_host_tensor, order=%d)" % (
+                   "Heat(G, 50)", order)) if world == 1 else
+                      "PartitionedCheby.filter_pinned(pinned host block of the rank's rows)",
+               "pipeline": "%d column chunks of %d signals: upload j+1 / recurrence j / download j-1 "
+                           "on three streams (strided 2-D copies by %s)" % (
+                               nsig // wchunk, wchunk,
+                               "a zero-copy kernel" if os.environ.get("GSPB200_STAGE") == "kernel"
+                               else "the copy engines"),
+               "max_abs_diff_vs_device_path_rel": e2e_err, "numa_cpus_bound": numa_cpus}
+        del xh, yh
 
-    nnz_all = torch.tensor([nnz], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(nnz_all)
+    # ---- parity legs
+    parity = {}
+    if world > 1 and G is not None:
+        # every rank owns the whole graph: the partitioned result must equal the one-GPU
+        # engine's on the rank's rows (same kernels, same summation order: expected 0.0)
+        single = device_op(apx, G.L, lmax, c)
+        full = single(x_full)
+        mine = run_dev(x)
+        err = float((mine - full[:, lo:lo + n]).abs().max() / full.abs().max())
+        parity["parity_rel_err"] = allmax(err)
+        parity["parity_bit_identical_on_every_rank"] = allmax(0.0 if torch.equal(
+            mine, full[:, lo:lo + n]) else 1.0) == 0.0
+        t_single = allmax(time_calls(torch, single, x_full, 3, 1))
+        parity["one_gpu_same_graph_ms_per_step"] = t_single
+        parity["speedup_vs_one_gpu_same_run"] = t_single / (1e3 * t_dev / args.steps)
+        del full, mine
+        if rank == 0:        # and the engine itself against the float64 oracle on one column
+            col = x_full[:, :1].contiguous()
+            parity["parity_rel_err_one_column_vs_oracle"] = oracle_parity(G.L, lmax, c, col, single(col))
+    elif world > 1:
+        parity["parity_rel_err"] = None
+        parity["parity_note"] = "no rank holds the whole graph for this workload; see tests/"
+
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (one fused step, k >= 2), per GPU
-    b_first, b_step, b_call = algorithmic_bytes(n, nnz, nsig, wl["nscales"], order)
-    peak, peak_src = measured_peak()
+    # ---- roofline of the dominant kernel (one fused step), per GPU
+    b_first, b_step, b_call = algorithmic_bytes(n, nnz, nsig, wl["nscales"], order, clenshaw=clen)
+    _, _, b_call_ref = algorithmic_bytes(n, nnz, nsig, wl["nscales"], order, clenshaw=False)
     achieved = b_call * args.steps / t_dev / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "per_gpu": True,
+                "frac": achieved / peak, "traffic": ncu_traffic(name if world == 1 else None),
+                "per_gpu": True,
                 "kernel": "cheby_step_tiled (TMA-tiled fused step, csrc/cheby_tiled.cu)",
+                "form": ("clenshaw: 4 passes over the signal block per step" if clen else
+                         "forward: 3 + 2 Nscales passes per step"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b_step,
+                "algorithmic_bytes_per_call": b_call,
                 "avg_launch_ms": 1e3 * t_dev / args.steps * (b_step / b_call),
+                "frac_if_counted_with_the_reference_algorithm_bytes":
+                    b_call_ref * args.steps / t_dev / 1e9 / peak,
                 "timing": "CUDA events on the launching stream over the timed region, max over ranks"}
     # for a graph without locality the x_cur term of the algorithmic bytes
     # (each row once) is unattainable; the gather-aware figure charges every stored entry
@@ -473,62 +669,78 @@ def run_ours(args):
     roofline["gather_aware"] = {"bytes_per_launch": b_step + gather,
                                 "frac_if_no_gather_reuse": (b_call + order * gather) * args.steps
                                 / t_dev / 1e9 / peak}
-    if halo is not None:
-        halo_bytes = halo["rows_received_per_rank"] * nsig * 4
-        halo.update({"bytes_received_per_rank_per_step": halo_bytes,
-                     "nvlink_GBps_per_rank_if_serialised": halo_bytes * order * args.steps / t_dev / 1e9,
-                     "exchange": os.environ.get("GSPB200_EXCHANGE") or "p2p: peer stores over NVLink into the neighbours' halo rows + flag wait (csrc/halo.cu); NCCL all_to_all_single available with GSPB200_EXCHANGE=nccl"})
+    halo = None
+    if world > 1:
+        halo_bytes = op.plan.n_halo * nsig * 4
+        halo = {"rows_received_per_rank": op.plan.n_halo, "boundary_rows": op.plan.n_true_boundary,
+                "bytes_received_per_rank_per_step": halo_bytes,
+                "nvlink_GBps_per_rank_if_serialised": halo_bytes * order * args.steps / t_dev / 1e9,
+                "exchange": op._exchange_mode(nsig) + (
+                    ": peer stores over NVLink into the neighbours' halo rows from the step "
+                    "kernel's epilogue + flags (csrc/dist.cu, csrc/cheby_tiled.cu)"
+                    if op._exchange_mode(nsig) == "p2p" else
+                    ": pack + NCCL all_to_all_single, overlapped with the interior rows")}
 
-    # ---- CPU baseline (oracle port of the scipy path) on a bounded sample
+    # ---- CPU baseline (the reference's scipy path) on a bounded sample, rank 0, one GPU
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import pygsp_oracle as orc
         cols = args.cpu_columns
-        Lh = L.to_scipy().astype(np.float64)
         xs = x[:, :cols].double().cpu().numpy()
         if wl["bank"] == "heat":
             cref = CpuReference(G.W.to_scipy().astype(np.float64), lmax, wl["scale"], order, xs, 1)
             t_cpu, cpu_kind = cref.time_once(), cref.kind
         else:                                   # banks: time the oracle port of cheby_op
             t0 = time.perf_counter()
-            orc.cheby_op(Lh, lmax, c, xs)
+            orc.cheby_op(G.L.to_scipy().astype(np.float64), lmax, c, xs)
             t_cpu, cpu_kind = time.perf_counter() - t0, "port"
-        ref = orc.cheby_op(Lh, lmax, c, xs[:, :1])
-        got = apx.cheby_op_device(L, lmax, c, x[:, :1].contiguous()).reshape(-1, 1).cpu().numpy()
-        parity = float(np.abs(got - ref).max() / np.abs(ref).max())
+        col = x[:, :1].contiguous()
         cpu = {"value": n * cols * order / t_cpu, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                "host_cores_available": os.cpu_count(),
                "sample": "%d of %d signal columns, full graph, full order, float64; %s" % (
                    cols, nsig, "unmodified PyGSP 0.6.1 (baseline/_ref) g.filter()"
                    if cpu_kind == "reference" else "oracle port (scipy csr_matvecs + numpy)"),
-               "parity_rel_err_vs_gpu": parity}
+               "parity_rel_err_vs_gpu": oracle_parity(G.L, lmax, c, col, run_dev(col))}
+
+    # ---- the other BASELINE workloads that fit one GPU, short runs in the same line
+    targets = None
+    if world == 1 and name == "config2" and not args.no_targets:
+        del x_full, x, y_dev
+        torch.cuda.empty_cache()
+        targets = {}
+        for tname in ("knn10m", "config3"):
+            try:
+                targets[tname] = run_target(gsp, apx, torch, tname, peak)
+            except Exception as exc:                    # a failed side run must not lose the line
+                targets[tname] = {"error": repr(exc)[:300]}
+
+    # Lanczos timing on the workload's graph (estimate_lmax is part of the path)
+    lanczos = None
+    if G is not None and world == 1:
+        G._lmax_method = None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        G.estimate_lmax()
+        torch.cuda.synchronize()
+        lanczos = {"estimate_lmax_ms": 1e3 * (time.perf_counter() - t0),
+                   "spmv_products": G._lanczos_steps, "lmax": G.lmax}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": 1e3 * t_dev / args.steps,
-           "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-           "dtype": "f32",
-           "data": "synthetic",
-           "config": {"workload": wl["name"], "N_per_gpu": n, "N_global": world * n, "k": wl["k"],
-                      "nsig": nsig, "order": order, "nnz_L_global": int(nnz_all.item()),
-                      "lmax": lmax,
-                      "partition": "single GPU" if world == 1 else
-                                   "1-D vertex partition, %d row blocks (strips), halo all-to-all-v "
-                                   "per step" % world,
-                      "l2_policy": "inputs_exceed_l2 (working set %.2f GB per GPU per call >> 126 MB)"
-                                   % ((4 * n * nsig * 4 + 8 * nnz) / 1e9)},
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * nsig * world,
-                   "d2h_bytes_per_step": 4 * n * nsig * world * wl["nscales"],
-                   "ms_per_step": 1e3 * t_e2e / args.steps,
-                   "api": "%s.filter(pinned_host_tensor, order=%d)" % (
-                       "MexicanHat(G, Nf=6)" if wl["bank"] == "mexicanhat" else "Heat(G, 50)", order)
-                   if world == 1 else
-                          "PartitionedCheby.cheby_op(pinned host block -> H2D -> op -> D2H)"},
-           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "halo": halo,
+           "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": config_dict(wl, world, scaling),
+           "graph": {"nnz_L_global": int(nnz_global), "lmax": lmax, "build_s": t_build},
+           "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "halo": halo, "targets": targets, "estimate_lmax": lanczos,
            "clocks": clocks.summary(t_region0, t_region1)}
+    out.update(parity)
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if out.get("parity_rel_err") is not None and out["parity_rel_err"] > 1e-5:
+        raise SystemExit("parity check failed: %r" % out["parity_rel_err"])
 
 
 if __name__ == "__main__":

@@ -20,13 +20,14 @@
 #ifndef GSPB200_H_
 #define GSPB200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define GSPB200_ABI_VERSION 1
+#define GSPB200_ABI_VERSION 2
 
 int gsp_abi_version(void);
 const char* gsp_last_error(void);
@@ -64,7 +65,7 @@ typedef struct gsp_tile_plan {
   int slab_capacity;   /* CSR entries a stage can hold (>= the matrix's largest tile) */
   int stages;          /* depth of the TMA ring */
   int consumer_warps;  /* warps that compute (one more warp produces) */
-  int gather_unroll;   /* neighbour packets requested back to back */
+  int gather_unroll;   /* reserved (always 4: one LDS.128 group of CSR entries) */
   int blocks_per_sm;   /* 0 = as many as fit */
 } gsp_tile_plan;
 
@@ -72,13 +73,19 @@ typedef struct gsp_tile_plan {
 int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales,
                         gsp_tile_plan* plan_host_out, void* stream);
 
-/* Halo exchange fused into the tiled float32 step (vertex-partitioned path): the
- * kernel first waits until flags[wait_ids[q]] >= wait_value (the neighbours have stored
- * x_cur's halo rows into this GPU), stores every row < n_push_rows of x_new into
- * peer_base[push_peer[e]][push_row[e], :] for e in [push_ptr[row], push_ptr[row+1])
- * from its epilogue (peer stores over NVLink), and, when the last boundary tile is
- * done, writes publish_value to every peer_flags[q].  All pointers are device pointers;
- * the struct itself is a host struct.  n_push_tiles is filled in by the library. */
+/* Halo exchange fused into the tiled float32 step (vertex-partitioned path).  Local rows
+ * are ordered boundary-first: rows [0, n_boundary_rows) may reference halo columns
+ * (column ids >= n_owned), rows [0, n_push_rows) are needed by some neighbour.  The kernel
+ * runs the tiles that hold such rows first.  Only the warps that work on a tile with boundary
+ * rows wait until flags[wait_ids[q]] >= wait_value (the neighbours have stored x_cur's halo
+ * rows into this GPU; those rows are read through L2, never through the non-coherent
+ * path); interior tiles start at once.  Every row < n_push_rows of x_new is stored into
+ * peer_base[push_peer[e]][push_row[e], :] for e in [push_ptr[row], push_ptr[row+1]) from
+ * the epilogue (peer stores over NVLink).  With publish != 0, publish_value is written to
+ * every peer_flags[q] when the last front tile is done -- at that point the pushed rows are
+ * visible and nobody on this GPU reads the halo of x_cur any more, so the neighbours may
+ * also overwrite it.  All pointers are device pointers; the struct itself is a host
+ * struct.  n_push_tiles / n_wait_tiles are filled in by the library. */
 typedef struct gsp_halo_fusion {
   int64_t n_push_rows;
   int64_t n_push_tiles;
@@ -94,17 +101,24 @@ typedef struct gsp_halo_fusion {
   uint64_t wait_value;
   int32_t n_neighbors;
   int32_t n_wait;
+  int64_t n_boundary_rows;         /* rows [0, n_boundary_rows) may read halo columns */
+  int64_t n_wait_tiles;
+  int64_t n_owned;                 /* columns >= n_owned are halo rows of x_cur */
+  int32_t publish;                 /* 0: last step of a call, nothing is published */
+  int32_t reserved;
 } gsp_halo_fusion;
 
 /* One fused step on the whole local row block with the halo exchange folded in
- * (float32, tiled kernel required: returns -3 when no tile plan applies). */
+ * (float32, tiled kernel required: returns -3 when no tile plan applies).  reverse != 0
+ * walks the interior tiles from the last to the first (alternate it between steps: the
+ * lines a step wrote last are then the first ones the next step reads, still in L2). */
 int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_t* indptr,
                             const int32_t* indices, const float* data, const float* x_cur,
                             const float* x_old, float* x_new, float* r, int64_t r_rows,
                             int64_t nsig, int nscales, const double* ck_host,
                             const double* c0_host, double alpha, double beta, double gamma,
-                            const gsp_tile_plan* plan_host, const gsp_halo_fusion* halo_host,
-                            void* stream);
+                            int reverse, const gsp_tile_plan* plan_host,
+                            const gsp_halo_fusion* halo_host, void* stream);
 
 #define GSPB200_DECLARE_CHEBY_API(SUF, T)                                                         \
   int gsp_cheby_op_##SUF(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,   \
@@ -129,18 +143,27 @@ GSPB200_DECLARE_CHEBY_API(f32, float)
 GSPB200_DECLARE_CHEBY_API(f64, double)
 
 /* ------------------------------------------------------------------- lmax ---
+ * gsp_spmv_*: y = L x for ONE vector -- scipy's csr_matvec, the product ARPACK calls at
+ *   pygsp/graphs/graph.py:911-917 and the one of graph.py:955.  2..32 lanes per row (from the
+ *   mean row length), coalesced reads of indices / data, warp-shuffle reduction per row.
  * gsp_lanczos_*: pygsp/graphs/graph.py:911-917 (scipy eigsh -> ARPACK).
- *   Runs Lanczos iterations [j0, j1) on L.  V3 holds 3*n elements, scal_dev
- *   2*cap+4096 doubles: alpha[0..cap) | beta[0..cap) | reduction partials.  j0 == 0 seeds the
- *   start vector from `seed` (counter-based, reproducible).  The host reads
- *   alpha/beta back and diagonalises the tridiagonal matrix.
+ *   Runs Lanczos iterations [j0, j1) on L: two launches per iteration (the SpMV above with
+ *   the v'Lv dot product fused in; the three-term update fused with the norm).  V3 holds
+ *   3*n elements, scal_dev 2*cap+1+4096 doubles: alpha[0..cap) | beta[-1..cap) | reduction
+ *   partials (beta[j] couples v_j and v_{j+1}; beta[-1] is the norm of the start vector).
+ *   j0 == 0 seeds the start vector from `seed` (counter-based, reproducible).  The host
+ *   reads alpha/beta back and diagonalises the tridiagonal matrix.
  */
-int gsp_lanczos_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
-                    float* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
-                    void* stream);
-int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                    double* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
-                    void* stream);
+int gsp_spmv_f32(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                 const float* data, const float* x, float* y, void* stream);
+int gsp_spmv_f64(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                 const double* data, const double* x, double* y, void* stream);
+int gsp_lanczos_f32(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                    const float* data, float* V3, int j0, int j1, int cap, uint64_t seed,
+                    double* scal_dev, void* stream);
+int gsp_lanczos_f64(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                    const double* data, double* V3, int j0, int j1, int cap, uint64_t seed,
+                    double* scal_dev, void* stream);
 
 /* ------------------------------------------------------------------ graph ---
  * gsp_coo_to_csr_*    graph.py:109  sparse.csr_matrix(coo): sort by (row, col), sum duplicates.
@@ -163,6 +186,21 @@ int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, co
  * gsp_gather_rows_* / gsp_scatter_rows_*  dst[i,:] = src[idx[i],:] / dst[idx[i],:] = src[i,:]
  *     (vertex reordering in and out, halo packing).
  */
+/* ------------------------------------------------- host <-> device staging ---
+ * Filter.filter() takes and returns host arrays (filter.py:146-328).  To overlap the PCIe
+ * transfers with the recurrence the signal block is processed in COLUMN chunks; a chunk of a
+ * row-major (n, nsig) block is a strided 2-D region (`height` rows of `width_bytes`, row
+ * pitches in bytes).
+ * gsp_copy2d_async: cudaMemcpy2DAsync on `stream` (copy engines); kind 1 = host to device,
+ *   2 = device to host, 3 = device to device.  Host memory must be page-locked.
+ * gsp_stage_cols: the same region moved by a kernel of at most max_blocks blocks (0 = one
+ *   per SM) that reads / writes PINNED host memory through its unified address; all
+ *   pointers, pitches and width_bytes must be multiples of 16. */
+int gsp_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                     size_t height, int kind, void* stream);
+int gsp_stage_cols(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                   size_t height, int max_blocks, void* stream);
+
 /* ------------------------------------------------------------ peer-memory halo ---
  * The vertex-partitioned path (no reference counterpart: PyGSP is single-process).
  * gsp_ipc_alloc / open / close / free: cudaMalloc'ed, zero-filled buffers exported with
@@ -187,6 +225,66 @@ int gsp_halo_push_f64(int64_t n_send, const int64_t* src_row, const int32_t* dst
                       uint64_t value, uint32_t* done_counter, void* stream);
 int gsp_halo_wait(const uint64_t* flags, const int32_t* neighbor_ids, int n_neighbors,
                   uint64_t value, void* stream);
+
+/* ------------------------------------------- the partitioned operator, one call ---
+ * gsp_cheby_op_dist_*: approximations.py:58-114 on ONE rank's row block of a 1-D vertex
+ * partitioned Laplacian.  The caller (one process per GPU) builds the plan
+ * once -- which of its rows every neighbour needs and where they live in the neighbour's
+ * halo, the CUDA-IPC mapped state buffers and flag arrays; that is host-side set-up and
+ * needs the job's communicator once (pygsp_b200/distributed.py: HaloPlan, PeerWindow) --
+ * and then runs any number of calls without any collective: each of the K recurrence
+ * steps waits for the neighbours' flags, computes, stores its boundary rows into the
+ * neighbours' halo rows over NVLink and publishes the step (all inside the fused step
+ * kernel for float32 with a tile plan; wait / step / push kernels otherwise).
+ *
+ *   local rows are ordered boundary-first (rows [0, n_boundary_rows) reference halo
+ *   columns, rows [0, n_push_rows) are needed by neighbours); local column j < n_local is
+ *   local row j, column n_local + h is halo slot h.
+ *   buf[b]        : this rank's state buffers, (n_local + n_halo, nsig) each, inside its IPC
+ *                   window; buf[2] may be NULL (then the Clenshaw form is not used)
+ *   peer_base[b]  : device array of P pointers, entry q = rank q's buf[b] (mapped)
+ *   peer_flags[i] : device array, entry i = address of THIS rank's slot in the flag array
+ *                   of neighbour neighbor_ids[i]; flags = this rank's own flag array (P slots)
+ *   src_row/dst_peer/dst_row (n_send entries): the rows to push as a flat list;
+ *   push_ptr/push_peer/push_row: the same list as a CSR over local rows [0, n_push_rows)
+ *   push_counter / fused_counter: zero-initialised device counters owned by the caller
+ *   x : (n_local, nsig) input in LOCAL row order (NULL: already in buf[0]);
+ *   r : (nscales, n_local, nsig) output, local row order;
+ *   clenshaw != 0 and nscales == 1: backward (Clenshaw) recurrence, one pass less per order;
+ *   seq_host : the rank's sequence counter (starts at 0, advanced by m + 2 per call; all
+ *              ranks must make the same calls in the same order).
+ * Everything is enqueued on `stream`; nothing synchronises. */
+typedef struct gsp_dist_plan {
+  int64_t n_local, n_halo, nnz;
+  const int32_t* indptr;
+  const int32_t* indices;
+  const void* data;                  /* float / double values of the local CSR */
+  void* buf[3];
+  void* const* peer_base[3];
+  uint64_t* const* peer_flags;
+  uint64_t* flags;
+  const int32_t* neighbor_ids;
+  int32_t n_neighbors;
+  int32_t reserved;
+  uint32_t* push_counter;
+  uint64_t* fused_counter;
+  int64_t n_send;
+  const int64_t* src_row;
+  const int32_t* dst_peer;
+  const int64_t* dst_row;
+  int64_t n_push_rows;
+  const int32_t* push_ptr;
+  const int32_t* push_peer;
+  const int64_t* push_row;
+  int64_t n_boundary_rows;
+} gsp_dist_plan;
+
+int gsp_cheby_op_dist_f32(const gsp_dist_plan* plan_host, const gsp_tile_plan* tile_host,
+                          double lmax, const double* coeffs_host, int nscales, int m, const float* x,
+                          int64_t nsig, float* r, int clenshaw, uint64_t* seq_host, void* stream);
+int gsp_cheby_op_dist_f64(const gsp_dist_plan* plan_host, const gsp_tile_plan* tile_host,
+                          double lmax, const double* coeffs_host, int nscales, int m, const double* x,
+                          int64_t nsig, double* r, int clenshaw, uint64_t* seq_host, void* stream);
 
 /* ------------------------------------------------------ on-device graph construction ---
  * gsp_grid2d_*: adjacency of pygsp/graphs/grid2d.py:40-89 (n1 x n2 grid, 4 neighbours, unit

@@ -38,7 +38,25 @@ class HaloFusion(ctypes.Structure):
                 ("peer_flags", ctypes.c_void_p), ("push_counter", ctypes.c_void_p),
                 ("wait_flags", ctypes.c_void_p), ("wait_ids", ctypes.c_void_p),
                 ("publish_value", ctypes.c_uint64), ("wait_value", ctypes.c_uint64),
-                ("n_neighbors", ctypes.c_int32), ("n_wait", ctypes.c_int32)]
+                ("n_neighbors", ctypes.c_int32), ("n_wait", ctypes.c_int32),
+                ("n_boundary_rows", ctypes.c_int64), ("n_wait_tiles", ctypes.c_int64),
+                ("n_owned", ctypes.c_int64), ("publish", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class DistPlan(ctypes.Structure):
+    """Mirror of ``gsp_dist_plan`` (include/gspb200.h)."""
+    _fields_ = [("n_local", ctypes.c_int64), ("n_halo", ctypes.c_int64), ("nnz", ctypes.c_int64),
+                ("indptr", ctypes.c_void_p), ("indices", ctypes.c_void_p), ("data", ctypes.c_void_p),
+                ("buf", ctypes.c_void_p * 3), ("peer_base", ctypes.c_void_p * 3),
+                ("peer_flags", ctypes.c_void_p), ("flags", ctypes.c_void_p),
+                ("neighbor_ids", ctypes.c_void_p), ("n_neighbors", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("push_counter", ctypes.c_void_p),
+                ("fused_counter", ctypes.c_void_p), ("n_send", ctypes.c_int64),
+                ("src_row", ctypes.c_void_p), ("dst_peer", ctypes.c_void_p),
+                ("dst_row", ctypes.c_void_p), ("n_push_rows", ctypes.c_int64),
+                ("push_ptr", ctypes.c_void_p), ("push_peer", ctypes.c_void_p),
+                ("push_row", ctypes.c_void_p), ("n_boundary_rows", ctypes.c_int64)]
 
 
 def header_symbols():
@@ -68,7 +86,7 @@ def lib():
             raise NativeError("cannot load %s: %s" % (path, exc))
         _lib.gsp_last_error.restype = ctypes.c_char_p
         _lib.gsp_abi_version.restype = ctypes.c_int
-        if _lib.gsp_abi_version() != 1:
+        if _lib.gsp_abi_version() != 2:
             raise NativeError("libgspb200 ABI mismatch")
     return _lib
 
@@ -77,7 +95,7 @@ def _arg(a):
     """torch tensor -> device pointer; None -> NULL; numpy -> host pointer."""
     if a is None:
         return ctypes.c_void_p(0)
-    if isinstance(a, (TilePlan, HaloFusion)):
+    if isinstance(a, (TilePlan, HaloFusion, DistPlan)):
         return ctypes.byref(a)
     if hasattr(a, "data_ptr"):
         return ctypes.c_void_p(a.data_ptr())

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libgspb200.so")
-SOURCES = ["runtime.cu", "cheby.cu", "cheby_tiled.cu", "graph.cu", "lanczos.cu", "halo.cu", "generate.cu"]
+SOURCES = ["runtime.cu", "cheby.cu", "cheby_tiled.cu", "graph.cu", "lanczos.cu", "halo.cu", "generate.cu", "staging.cu", "dist.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -32,7 +32,20 @@ def _stamp():
 
 
 def build(force=False, verbose=False):
+    """Build (if the sources changed) and return the path of the library.  One process at a
+    time (flock on _lib/.lock: torchrun starts one process per GPU on the same tree); objects
+    and the library are written under temporary names and renamed into place."""
+    import fcntl
     os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp_file = os.path.join(OUT_DIR, "stamp.txt")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file):
@@ -56,10 +69,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", *ARCH, "-o", LIB, *objs]
-    subprocess.check_call(cmd)
-    with open(stamp_file, "w") as fh:
+    tmp_lib = LIB + ".tmp.%d" % os.getpid()
+    subprocess.check_call([nvcc, "-shared", *ARCH, "-o", tmp_lib, *objs])
+    os.replace(tmp_lib, LIB)
+    with open(stamp_file + ".tmp", "w") as fh:
         fh.write(stamp)
+    os.replace(stamp_file + ".tmp", stamp_file)
     return LIB
 
 

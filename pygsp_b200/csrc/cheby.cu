@@ -497,8 +497,8 @@ int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_
                             const float* x_old, float* x_new, float* r, int64_t r_rows,
                             int64_t nsig, int nscales, const double* ck_host,
                             const double* c0_host, double alpha, double beta, double gamma,
-                            const gsp_tile_plan* plan_host, const gsp_halo_fusion* halo_host,
-                            void* stream) {
+                            int reverse, const gsp_tile_plan* plan_host,
+                            const gsp_halo_fusion* halo_host, void* stream) {
   if (!(plan_host && plan_host->rows_per_tile > 0 && halo_host))
     return gsp::fail(GSP_ERR_UNSUPPORTED, "fused halo step needs a tile plan (%s)", "plan");
   GSP_REQUIRE(nscales <= gsp::kMaxScales, "too many filters for the fused step");
@@ -506,7 +506,7 @@ int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_
   int rc = gsp::cheby_step_tiled_f32(first != 0, 0, n_rows, nnz, indptr, indices, data, x_cur,
                                      x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
                                      c0_host, alpha, beta, gamma, *plan_host, halo_host, &done,
-                                     gsp::as_stream(stream));
+                                     gsp::as_stream(stream), false, reverse != 0);
   if (rc != GSP_OK) return rc;
   // remainder rows (< rows_per_tile, interior by construction) with the row-group kernel
   return gsp::cheby_step<float>(first != 0, done, n_rows, indptr, indices, data, x_cur, x_old,

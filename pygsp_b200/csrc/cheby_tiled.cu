@@ -61,7 +61,7 @@ struct TileArgs {
   int l2_hint;            // evict-first hint on the streamed TMA copies
   int keep_writes;        // plain instead of evict-first stores for x_new / r
   int reverse;            // walk the tiles from the last to the first (see cheby_op)
-  int stage_xcur;         // stage the tile's own x_cur rows (XS variant)
+  int64_t n_front;        // tiles [0, n_front) always run first, in order (halo: boundary tiles)
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
 };
 
@@ -137,11 +137,8 @@ struct TileLayout {
   int ptr_bytes;      // indptr slab + trailing slot
   int stage_bytes;
   int bar_bytes;
-  int xs_offset;      // float offset of the staged x_cur tile inside the vec area
-  __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages,
-                                 bool xs = false) {
-    xs_offset = first ? 0 : (1 + nscales) * R * nsig;
-    vec_bytes = (xs_offset + (xs ? R * nsig : 0)) * 4;
+  __host__ __device__ TileLayout(int R, int cap, int nsig, int nscales, bool first, int stages) {
+    vec_bytes = first ? 0 : (1 + nscales) * R * nsig * 4;
     slab_bytes = (cap + 16) * 4;                // +16: aligned groups may run past the end
     ptr_bytes = (R + 4) * 4;
     stage_bytes = vec_bytes + 2 * slab_bytes + ptr_bytes + 16;   // +16: slab offset, group counter
@@ -150,17 +147,35 @@ struct TileLayout {
   __host__ __device__ int total(int stages) const { return bar_bytes + stages * stage_bytes; }
 };
 
-// XS: the tile's own x_cur rows are staged too and neighbours that fall inside the tile
-// are read from shared memory instead of L1 (experimental, GSPB200_TILE_XS=1).
-template <int G, int U, bool FIRST, int NSC, bool XS>
-__global__ void __launch_bounds__(32 * 17, U != 1 ? 1 : 2)
+// Order in which the persistent CTAs visit the tiles.  Tiles [0, n_front) come first, in
+// order (vertex-partitioned path: the boundary tiles, whose rows the neighbours wait for);
+// the others are walked forwards or backwards (`reverse`: the lines the previous step wrote
+// last are still in L2 and are the first ones this step reads).
+__device__ __forceinline__ int64_t tile_of_slot(const TileArgs& a, int64_t slot) {
+  if (slot < a.n_front) return slot;
+  return a.reverse ? a.n_tiles - 1 - (slot - a.n_front) : slot;
+}
+
+// halo rows of x_cur are written by the neighbours (peer stores) while this kernel may
+// already be running: they are read through L2 (ld.global.cg), never through the
+// non-coherent path.  Rows this GPU owns are read-only for the whole launch: ld.global.nc.
+template <bool HALO>
+__device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int col, int ns,
+                                            int n_owned) {
+  const float* p = xg + int64_t(col) * ns;
+  if (HALO && col >= n_owned) return __ldcg(reinterpret_cast<const float4*>(p));
+  return ldg_f4(p);
+}
+
+template <int G, bool FIRST, int NSC, bool HALO>
+__global__ void __launch_bounds__(32 * 17, 2)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.rows_per_tile;
   const int S = a.stages;
   const int NW = a.consumer_warps;
   const int nsig = a.nsig;
-  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S, XS);
+  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + S;
   unsigned char* stage0 = smem + lay.bar_bytes;
@@ -168,16 +183,6 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // Halo of x_cur: written by the neighbours' previous step straight into this
-  // GPU's memory; they published `wait_value` after their stores were fenced.
-  if (a.halo.n_wait > 0 && int(threadIdx.x) < a.halo.n_wait) {
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.halo.wait_flags) +
-                                  a.halo.wait_ids[threadIdx.x];
-    unsigned long long seen;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-    } while (seen < a.halo.wait_value);
-  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -189,6 +194,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------------------- producer
+    // (nothing the producer stages depends on the halo: CSR slabs, x_old and r rows are local)
     if (lane != 0) return;
     // x_old / r / CSR are touched once per step: mark them evict-first so that the
     // L2 keeps the x_cur lines the gathers re-use (GSPB200_TILE_HINT=0 disables)
@@ -199,19 +205,17 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     // DRAM latency is not in series with the wait for a free slot
     int nbegin = 0, nend = 0;
     if (int64_t(blockIdx.x) < a.n_tiles) {
-      const int64_t first_tile = a.reverse ? a.n_tiles - 1 - int64_t(blockIdx.x) : int64_t(blockIdx.x);
-      const int64_t rn = a.row_begin + first_tile * R;
+      const int64_t rn = a.row_begin + tile_of_slot(a, blockIdx.x) * R;
       nbegin = __ldg(a.indptr + rn);
       nend = __ldg(a.indptr + rn + R);
     }
     for (int64_t slot = blockIdx.x; slot < a.n_tiles; slot += gridDim.x, ++it) {
-      const int64_t tile = a.reverse ? a.n_tiles - 1 - slot : slot;
+      const int64_t tile = tile_of_slot(a, slot);
       const int s = it % S;
       const uint32_t round = uint32_t(it / S);
       const int begin = nbegin, end = nend;
       if (slot + gridDim.x < a.n_tiles) {
-        const int64_t nslot = slot + gridDim.x;
-        const int64_t rn = a.row_begin + (a.reverse ? a.n_tiles - 1 - nslot : nslot) * R;
+        const int64_t rn = a.row_begin + tile_of_slot(a, slot + gridDim.x) * R;
         nbegin = __ldg(a.indptr + rn);
         nend = __ldg(a.indptr + rn + R);
       }
@@ -236,10 +240,9 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const uint32_t slab = a1 > a0 ? uint32_t(a1 - a0) * 4u : 0u;
       const uint32_t tile_vec = uint32_t(R) * nsig * 4u;
       const uint32_t bytes = uint32_t(R) * 4u + 2u * slab +
-                             (FIRST ? 0u : tile_vec * (1 + a.nscales)) + (XS ? tile_vec : 0u);
+                             (FIRST ? 0u : tile_vec * (1 + a.nscales));
       mbar_expect_tx(full + s, bytes);
       bulk_g2s(sm_ptr, a.indptr + r0, uint32_t(R) * 4u, full + s);
-      if (XS) bulk_g2s(sm_vec + lay.xs_offset, a.x_cur + r0 * nsig, tile_vec, full + s);
       if (hint) {
         if (slab) {
           bulk_g2s_hint(sm_col, a.indices + a0, slab, full + s, pol);
@@ -277,11 +280,29 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   const int nscales = NSC >= 0 ? NSC : a.nscales;
   const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
   const bool keep_writes = a.keep_writes != 0;
+  const int n_owned = HALO ? int(a.halo.n_owned) : 0;
+  bool halo_seen = !(HALO && a.halo.n_wait > 0);
   int it = 0;
   for (int64_t slot = blockIdx.x; slot < a.n_tiles; slot += gridDim.x, ++it) {
-    const int64_t tile = a.reverse ? a.n_tiles - 1 - slot : slot;
+    const int64_t tile = tile_of_slot(a, slot);
     const int s = it % S;
     const uint32_t round = uint32_t(it / S);
+    if (HALO && !halo_seen && tile < a.halo.n_wait_tiles) {
+      // First tile of this warp whose rows reference halo columns: the neighbours must have
+      // published the halo of x_cur (they stored it straight into this GPU's memory and
+      // released wait_value afterwards).  Interior tiles never come here, so a CTA that
+      // owns interior tiles only does not wait at all.
+      if (lane < a.halo.n_wait) {
+        const unsigned long long* f =
+            reinterpret_cast<const unsigned long long*>(a.halo.wait_flags) + a.halo.wait_ids[lane];
+        unsigned long long seen;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+        } while (seen < a.halo.wait_value);
+      }
+      __syncwarp();
+      halo_seen = true;
+    }
     mbar_wait(full + s, round & 1u);
     unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
     const float* sm_vec = reinterpret_cast<const float*>(st);
@@ -290,9 +311,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
     const int a0 = sm_ptr[R + 4];
     const int64_t r0 = a.row_begin + tile * R;
-    const bool push_tile = tile < a.halo.n_push_tiles;      // warp-uniform
-    const int tile_row0 = int(r0);
-    const float* sm_x = sm_vec + lay.xs_offset + c0;
+    const bool push_tile = HALO && tile < a.halo.n_push_tiles;      // warp-uniform
     const float* __restrict__ xc_tile = xg + r0 * NS;
     float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
     float* __restrict__ r_tile = a.r + r0 * NS + c0;
@@ -303,55 +322,34 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
       const unsigned span = unsigned(je - jb);
-      const float4 xc = XS ? *reinterpret_cast<const float4*>(sm_vec + lay.xs_offset + off + c0)
-                           : ldg_f4(xc_tile + off);
+      const float4 xc = ldg_f4(xc_tile + off);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       // The slab offset a0 is a multiple of 4, so groups of four CSR entries are
       // 16-byte aligned in shared memory: one LDS.128 brings four column indices,
       // one four weights.  Slots outside [jb, je) (row head / tail) are predicated
       // off, so the sum runs over the row's entries in stored order.
-      for (int jj = jb & ~3; jj < je; jj += 4 * U) {
-        int4 c4[U];
-        float4 w4[U];
-        float4 xv[4 * U];
-        bool ok[4 * U];
+      for (int jj = jb & ~3; jj < je; jj += 4) {
+        const int4 c4 = *reinterpret_cast<const int4*>(sm_col + jj);
+        const float4 w4 = *reinterpret_cast<const float4*>(sm_val + jj);
+        float4 xv[4];
+        bool ok[4];
+        const int base = jj - jb;
+        ok[0] = unsigned(base + 0) < span;
+        ok[1] = unsigned(base + 1) < span;
+        ok[2] = unsigned(base + 2) < span;
+        ok[3] = unsigned(base + 3) < span;
+        const int cq[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          c4[u] = *reinterpret_cast<const int4*>(sm_col + jj + 4 * u);
-          w4[u] = *reinterpret_cast<const float4*>(sm_val + jj + 4 * u);
-        }
+        for (int q = 0; q < 4; ++q)
+          if (ok[q]) xv[q] = gather_f4<HALO>(xg, cq[q], NS, n_owned);
+        const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int base = jj + 4 * u - jb;
-          ok[4 * u + 0] = unsigned(base + 0) < span;
-          ok[4 * u + 1] = unsigned(base + 1) < span;
-          ok[4 * u + 2] = unsigned(base + 2) < span;
-          ok[4 * u + 3] = unsigned(base + 3) < span;
-          const int cq[4] = {c4[u].x, c4[u].y, c4[u].z, c4[u].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (!ok[4 * u + q]) continue;
-            if (XS) {
-              const unsigned rel = unsigned(cq[q] - tile_row0);
-              if (rel < unsigned(R)) {
-                xv[4 * u + q] = *reinterpret_cast<const float4*>(sm_x + rel * NS);
-                continue;
-              }
-            }
-            xv[4 * u + q] = ldg_f4(xg + int64_t(cq[q]) * NS);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float wq[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (ok[4 * u + q]) {
-              acc.x = fmaf(wq[q], xv[4 * u + q].x, acc.x);
-              acc.y = fmaf(wq[q], xv[4 * u + q].y, acc.y);
-              acc.z = fmaf(wq[q], xv[4 * u + q].z, acc.z);
-              acc.w = fmaf(wq[q], xv[4 * u + q].w, acc.w);
-            }
+        for (int q = 0; q < 4; ++q) {
+          if (ok[q]) {
+            acc.x = fmaf(wq[q], xv[q].x, acc.x);
+            acc.y = fmaf(wq[q], xv[q].y, acc.y);
+            acc.z = fmaf(wq[q], xv[q].z, acc.z);
+            acc.w = fmaf(wq[q], xv[q].w, acc.w);
           }
         }
       }
@@ -417,8 +415,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       }
     }
     if (push_tile) {
-      // all boundary tiles done (every warp of every CTA checks in once per tile):
-      // publish the step to the neighbours
+      // Every warp of every CTA checks in once per front tile.  When the last one has, (a) all
+      // boundary rows of x_new are stored in the neighbours and (b) nobody on this GPU reads
+      // the halo of x_cur any more (only front tiles do): publish the step.  The neighbours
+      // then may both read their halo of x_new and overwrite our halo of x_cur's buffer.
       __threadfence_system();
       __syncwarp();
       if (lane == 0) {
@@ -508,12 +508,12 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   return GSP_OK;
 }
 
-template <int G, int U, int NSC, bool XS>
+template <int G, int NSC, bool HALO>
 static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
-  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages, XS);
+  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages);
   const int smem = lay.total(a.stages);
   const int threads = 32 * (1 + a.consumer_warps);
-  auto kern = first ? cheby_step_tiled<G, U, true, NSC, XS> : cheby_step_tiled<G, U, false, NSC, XS>;
+  auto kern = first ? cheby_step_tiled<G, true, NSC, HALO> : cheby_step_tiled<G, false, NSC, HALO>;
   GSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
   GSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -525,22 +525,20 @@ static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cuda
   return GSP_OK;
 }
 
-template <int G, int U, bool XS>
-static int launch_tiled_gu(bool first, const TileArgs& a, int bps, cudaStream_t st) {
+template <int G, bool HALO>
+static int launch_tiled_gh(bool first, const TileArgs& a, int bps, cudaStream_t st) {
   switch (a.nscales) {          // common bank widths get the scale loop unrolled
-    case 0: return launch_tiled_k<G, U, 0, XS>(first, a, bps, st);
-    case 1: return launch_tiled_k<G, U, 1, XS>(first, a, bps, st);
-    case 2: return launch_tiled_k<G, U, 2, XS>(first, a, bps, st);
-    default: return launch_tiled_k<G, U, -1, XS>(first, a, bps, st);
+    case 0: return launch_tiled_k<G, 0, HALO>(first, a, bps, st);
+    case 1: return launch_tiled_k<G, 1, HALO>(first, a, bps, st);
+    case 2: return launch_tiled_k<G, 2, HALO>(first, a, bps, st);
+    default: return launch_tiled_k<G, -1, HALO>(first, a, bps, st);
   }
 }
 
 template <int G>
-static int launch_tiled_g(bool first, const TileArgs& a, int unroll, int bps, cudaStream_t st) {
-  // `unroll` = neighbour packets requested back to back: 4 or 8 (groups of four entries)
-  if (unroll >= 8) return launch_tiled_gu<G, 2, false>(first, a, bps, st);
-  return a.stage_xcur ? launch_tiled_gu<G, 1, true>(first, a, bps, st)
-                      : launch_tiled_gu<G, 1, false>(first, a, bps, st);
+static int launch_tiled_g(bool first, const TileArgs& a, bool halo, int bps, cudaStream_t st) {
+  return halo ? launch_tiled_gh<G, true>(first, a, bps, st)
+              : launch_tiled_gh<G, false>(first, a, bps, st);
 }
 
 // Full tiles of rows [rb, re) of one step (rb % 4 == 0); reports the number of rows done.
@@ -552,22 +550,29 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse) {
   TileArgs a;
   a.keep_writes = env_int("GSPB200_TILE_REV", 1);
-  a.reverse = (reverse && a.keep_writes && !halo) ? 1 : 0;
+  a.reverse = (reverse && a.keep_writes) ? 1 : 0;
   a.add_source = add_source ? 1 : 0;
   a.l2_hint = env_int("GSPB200_TILE_HINT", 1);
-  a.stage_xcur = env_int("GSPB200_TILE_XS", 0);
+  a.n_front = 0;
   GSP_REQUIRE(!add_source || (nscales >= 1 && !first), "add_source needs source blocks");
   memset(&a.halo, 0, sizeof(a.halo));
+  const int64_t full_tiles = (re - rb) / plan.rows_per_tile;
   if (halo) {
     a.halo = *halo;
+    const int R = plan.rows_per_tile;
     GSP_REQUIRE(rb == 0, "fused halo push needs the whole row block in one launch");
-    a.halo.n_push_tiles = ceil_div(halo->n_push_rows, plan.rows_per_tile);
-    GSP_REQUIRE(a.halo.n_push_tiles <= (re - rb) / plan.rows_per_tile,
-                "boundary rows must lie inside the full tiles");
     GSP_REQUIRE(halo->n_wait <= 32, "at most 32 neighbours");
+    GSP_REQUIRE(halo->n_push_rows >= 0 && halo->n_boundary_rows >= 0, "negative row counts");
+    // tiles whose rows read halo columns wait for the neighbours' flags; the step is
+    // published once those AND the tiles that push rows are done (both sets are "front")
+    a.halo.n_wait_tiles = ceil_div(halo->n_boundary_rows, R);
+    a.halo.n_push_tiles =
+        halo->publish ? ceil_div(std::max(halo->n_push_rows, halo->n_boundary_rows), R) : 0;
+    a.n_front = std::max(a.halo.n_wait_tiles, a.halo.n_push_tiles);
+    GSP_REQUIRE(a.n_front <= full_tiles, "boundary rows must lie inside the full tiles");
   }
   a.row_begin = rb;
-  a.n_tiles = (re - rb) / plan.rows_per_tile;
+  a.n_tiles = full_tiles;
   *rows_done = a.n_tiles * plan.rows_per_tile;
   if (a.n_tiles == 0) return GSP_OK;
   a.r_rows = r_rows;
@@ -585,12 +590,13 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
     a.ck[i] = i < nscales ? float(ck[i]) : 0.f;
     a.half_c0[i] = (first && i < nscales) ? float(0.5 * c0[i]) : 0.f;
   }
+  const bool h = halo != nullptr;
   switch (nsig) {
-    case 8: return launch_tiled_g<2>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
-    case 16: return launch_tiled_g<4>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
-    case 32: return launch_tiled_g<8>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
-    case 64: return launch_tiled_g<16>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
-    case 128: return launch_tiled_g<32>(first, a, plan.gather_unroll, plan.blocks_per_sm, st);
+    case 8: return launch_tiled_g<2>(first, a, h, plan.blocks_per_sm, st);
+    case 16: return launch_tiled_g<4>(first, a, h, plan.blocks_per_sm, st);
+    case 32: return launch_tiled_g<8>(first, a, h, plan.blocks_per_sm, st);
+    case 64: return launch_tiled_g<16>(first, a, h, plan.blocks_per_sm, st);
+    case 128: return launch_tiled_g<32>(first, a, h, plan.blocks_per_sm, st);
   }
   return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 8, 16, 32, 64 or 128 (%s)", "nsig");
 }

@@ -64,49 +64,130 @@ __global__ void lanczos_seed_kernel(int64_t n, T* v, uint64_t seed, double* part
   if (threadIdx.x == 0) part_out[blockIdx.x] = acc;
 }
 
-// partial sums of w . v
-template <typename T>
-__global__ void lanczos_dot_kernel(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
-                                   double* part_out) {
-  double acc = 0;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += int64_t(gridDim.x) * blockDim.x)
-    acc += double(a[i]) * double(b[i]);
-  acc = block_allreduce(acc);
-  if (threadIdx.x == 0) part_out[blockIdx.x] = acc;
+// ------------------------------------------------------------------ SpMV
+// y = scale * (A x) with LPR lanes per row (LPR = 2..32, chosen from the mean row length):
+// the lanes of a row read consecutive CSR entries -- neighbouring rows' entries are
+// neighbours in memory, so a warp's accesses to indices / data are contiguous -- gather
+// x[col], and the row sum is reduced with warp shuffles (graph.py:911-917 spends its time
+// in exactly this product).  Optionally the kernel also leaves, per block, the partial sum
+// of y_i * (scale * x_i): the Lanczos alpha = v' L v comes out of the same pass.
+// scale = 1 / sqrt(sum(inv_norm2_parts)) when inv_norm2_parts is given (the vector x is
+// the unnormalised Lanczos vector u_j, see lanczos_run), else 1.
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kVecThreads)
+spmv_subwarp_kernel(int64_t n, const int32_t* __restrict__ indptr,
+                    const int32_t* __restrict__ indices, const T* __restrict__ vals,
+                    const T* __restrict__ x, T* __restrict__ y, const double* norm2_parts,
+                    int n_parts, double* beta_out, double* dot_parts) {
+  double scale = 1.0;
+  if (norm2_parts) {
+    const double nb = sqrt(sum_partials(norm2_parts, n_parts));
+    scale = nb > 0 ? 1.0 / nb : 0.0;
+    if (beta_out && blockIdx.x == 0 && threadIdx.x == 0) *beta_out = nb;
+  }
+  constexpr int RPB = kVecThreads / LPR;          // rows per block and pass
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  double dot = 0;
+  for (int64_t base = int64_t(blockIdx.x) * RPB; base < n; base += int64_t(gridDim.x) * RPB) {
+    const int64_t row = base + sub;                // the trip count is uniform over the block
+    const bool valid = row < n;
+    int start = 0, end = 0;
+    if (valid) {
+      start = __ldg(indptr + row);
+      end = __ldg(indptr + row + 1);
+    }
+    double acc = 0;
+    for (int j = start + lane; j < end; j += LPR)
+      acc += double(__ldg(vals + j)) * double(__ldg(x + __ldg(indices + j)));
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LPR);
+    if (valid && lane == 0) {
+      const double yi = acc * scale;
+      y[row] = T(yi);
+      if (dot_parts) dot += double(T(yi)) * (double(x[row]) * scale);
+    }
+  }
+  if (dot_parts) {                                 // uniform branch
+    dot = block_allreduce(dot);
+    if (threadIdx.x == 0) dot_parts[blockIdx.x] = dot;
+  }
 }
 
-// alpha = sum(part_in); w -= alpha v + beta_prev v_prev ; partial |w|^2 -> part_out
+static inline int spmv_lanes(int64_t n, int64_t nnz) {
+  const double mean = n > 0 ? double(nnz) / double(n) : 1.0;
+  int lpr = 2;
+  while (lpr < 32 && 2 * lpr <= mean) lpr *= 2;      // largest power of two <= mean, in [2, 32]
+  return lpr;
+}
+
+static inline int spmv_blocks(int64_t n, int lpr) {
+  const int64_t rpb = kVecThreads / lpr;
+  return (int)std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div(n, rpb), std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks)));
+}
+
 template <typename T>
-__global__ void lanczos_update_kernel(int64_t n, T* __restrict__ w, const T* __restrict__ v,
-                                      const T* __restrict__ v_prev, const double* part_in,
-                                      int parts, const double* beta_prev, double* alpha_out,
-                                      double* part_out) {
-  const double a = sum_partials(part_in, parts);
+static int spmv_launch(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                       const T* vals, const T* x, T* y, const double* norm2_parts, int n_parts,
+                       double* beta_out, double* dot_parts, int* blocks_out, cudaStream_t st) {
+  const int lpr = spmv_lanes(n, nnz);
+  const int blocks = spmv_blocks(n, lpr);
+  if (blocks_out) *blocks_out = blocks;
+#define GSP_SPMV(L)                                                                          \
+  spmv_subwarp_kernel<T, L><<<blocks, kVecThreads, 0, st>>>(n, indptr, indices, vals, x, y, \
+                                                             norm2_parts, n_parts, beta_out, \
+                                                             dot_parts)
+  switch (lpr) {
+    case 2: GSP_SPMV(2); break;
+    case 4: GSP_SPMV(4); break;
+    case 8: GSP_SPMV(8); break;
+    case 16: GSP_SPMV(16); break;
+    default: GSP_SPMV(32); break;
+  }
+#undef GSP_SPMV
+  GSP_LAUNCH_CHECK("spmv_subwarp");
+  return GSP_OK;
+}
+
+// ---------------------------------------------------------------- Lanczos
+// The recurrence is carried on UNNORMALISED vectors u_j (v_j = u_j / beta_{j-1}), so that an
+// iteration is two launches and no pass exists only to rescale a vector:
+//   spmv   : beta_{j-1} = |u_j| from the partials of the previous update; w = L v_j;
+//            partial sums of alpha_j = v_j' w                       (reads CSR + u_j, writes w)
+//   update : alpha_j = sum(partials); u_{j+1} = w - alpha_j v_j - beta_{j-1} v_{j-1};
+//            partial sums of |u_{j+1}|^2                            (3 reads, 1 write)
+template <typename T>
+__global__ void lanczos_update_kernel(int64_t n, T* __restrict__ w, const T* __restrict__ u,
+                                      const T* __restrict__ u_prev, const double* dot_parts,
+                                      int n_dot, const double* beta_j1, const double* beta_j2,
+                                      double* alpha_out, double* norm2_parts) {
+  const double a = sum_partials(dot_parts, n_dot);
   if (blockIdx.x == 0 && threadIdx.x == 0) *alpha_out = a;
-  const double b = beta_prev ? *beta_prev : 0.0;
+  const double b1 = *beta_j1;                                  // |u_j|
+  const double ca = b1 > 0 ? a / b1 : 0.0;                     // alpha_j v_j = (alpha_j / b1) u_j
+  double cb = 0.0;                                             // beta_{j-1} v_{j-1} = (b1 / b2) u_{j-1}
+  if (u_prev) {
+    const double b2 = *beta_j2;
+    cb = b2 > 0 ? b1 / b2 : 0.0;
+  }
   double acc = 0;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += int64_t(gridDim.x) * blockDim.x) {
-    double t = double(w[i]) - a * double(v[i]);
-    if (v_prev) t -= b * double(v_prev[i]);
-    w[i] = T(t);
-    acc += t * t;
+    double t = double(w[i]) - ca * double(u[i]);
+    if (u_prev) t -= cb * double(u_prev[i]);
+    const T ts = T(t);
+    w[i] = ts;
+    acc += double(ts) * double(ts);
   }
   acc = block_allreduce(acc);
-  if (threadIdx.x == 0) part_out[blockIdx.x] = acc;
+  if (threadIdx.x == 0) norm2_parts[blockIdx.x] = acc;
 }
 
-// beta = sqrt(sum(part_in)); w /= beta
-template <typename T>
-__global__ void lanczos_scale_kernel(int64_t n, T* w, const double* part_in, int parts,
-                                     double* beta_out) {
-  const double nb = sqrt(sum_partials(part_in, parts));
-  const double inv = nb > 0 ? 1.0 / nb : 0.0;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += int64_t(gridDim.x) * blockDim.x)
-    w[i] = T(double(w[i]) * inv);
-  if (beta_out && blockIdx.x == 0 && threadIdx.x == 0) *beta_out = nb;
+// beta_{j1-1} of the last iteration of a batch (the next spmv would compute it)
+__global__ void lanczos_finish_kernel(const double* norm2_parts, int n_parts, double* beta_out) {
+  const double nb = sqrt(sum_partials(norm2_parts, n_parts));
+  if (threadIdx.x == 0) *beta_out = nb;
 }
 
 static inline int vec_blocks(int64_t n) {
@@ -114,40 +195,41 @@ static inline int vec_blocks(int64_t n) {
                                 std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks));
 }
 
-// Iterations [j0, j1) of the recurrence.  V holds three n-vectors; the Lanczos
-// vector v_j lives in slot j % 3.
-// scal = alpha[0..cap) | beta[0..cap) | partials A[2048] | partials B[2048].
+// Iterations [j0, j1) of the recurrence.  V holds three n-vectors; u_j lives in slot j % 3.
+// scal = alpha[0..cap) | beta[-1..cap) (cap + 1 values, beta[-1] = |u_0|) | partials A[2048]
+//        | partials B[2048] | (n_a, n_b as doubles).
 template <typename T>
-int lanczos_run(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data, T* V,
-                int j0, int j1, int cap, uint64_t seed, double* scal, cudaStream_t st) {
+int lanczos_run(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                const T* data, T* V, int j0, int j1, int cap, uint64_t seed, double* scal,
+                cudaStream_t st) {
   GSP_REQUIRE(n >= 1 && j0 >= 0 && j1 <= cap && j0 <= j1, "bad Lanczos range");
   double* alpha = scal;
-  double* beta = scal + cap;
-  double* part_a = scal + 2 * cap;
+  double* beta = scal + cap + 1;                 // beta[-1] is valid
+  double* part_a = scal + 2 * cap + 1;
   double* part_b = part_a + kMaxVecBlocks;
   const int gb = vec_blocks(n);
-  double zero = 0;
   if (j0 == 0) {
-    GSP_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * (2 * cap + 2 * kMaxVecBlocks), st));
+    GSP_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * (2 * cap + 1 + 2 * kMaxVecBlocks), st));
     lanczos_seed_kernel<T><<<gb, kVecThreads, 0, st>>>(n, V, seed, part_b);
-    lanczos_scale_kernel<T><<<gb, kVecThreads, 0, st>>>(n, V, part_b, gb, nullptr);
-    note_launch(1);
     GSP_LAUNCH_CHECK("lanczos_seed");
   }
   for (int j = j0; j < j1; ++j) {
-    T* v = V + int64_t(j % 3) * n;
+    T* u = V + int64_t(j % 3) * n;
     T* w = V + int64_t((j + 1) % 3) * n;
-    const T* vp = j > 0 ? V + int64_t((j + 2) % 3) * n : nullptr;
-    // w = L v
-    int rc = cheby_step<T>(true, 0, n, indptr, indices, data, v, nullptr, w, w, n, 1, 0, &zero,
-                           &zero, 1.0, 0.0, 0.0, st);
+    const T* up = j > 0 ? V + int64_t((j + 2) % 3) * n : nullptr;
+    int sb = 0;
+    // w = L u_j / |u_j|, beta[j-1] = |u_j|, partials of alpha_j
+    int rc = spmv_launch<T>(n, nnz, indptr, indices, data, u, w, part_b, gb, beta + j - 1, part_a,
+                            &sb, st);
     if (rc != GSP_OK) return rc;
-    lanczos_dot_kernel<T><<<gb, kVecThreads, 0, st>>>(n, w, v, part_a);
-    lanczos_update_kernel<T><<<gb, kVecThreads, 0, st>>>(
-        n, w, v, vp, part_a, gb, j > 0 ? beta + j - 1 : nullptr, alpha + j, part_b);
-    lanczos_scale_kernel<T><<<gb, kVecThreads, 0, st>>>(n, w, part_b, gb, beta + j);
-    note_launch(2);
-    GSP_LAUNCH_CHECK("lanczos_step");
+    lanczos_update_kernel<T><<<gb, kVecThreads, 0, st>>>(n, w, u, up, part_a, sb, beta + j - 1,
+                                                         j > 0 ? beta + j - 2 : nullptr,
+                                                         alpha + j, part_b);
+    GSP_LAUNCH_CHECK("lanczos_update");
+  }
+  if (j1 > j0) {
+    lanczos_finish_kernel<<<1, kVecThreads, 0, st>>>(part_b, gb, beta + j1 - 1);
+    GSP_LAUNCH_CHECK("lanczos_finish");
   }
   return GSP_OK;
 }
@@ -155,16 +237,29 @@ int lanczos_run(int64_t n, const int32_t* indptr, const int32_t* indices, const 
 }  // namespace gsp
 
 extern "C" {
-int gsp_lanczos_f32(int64_t n, const int32_t* indptr, const int32_t* indices, const float* data,
-                    float* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
-                    void* stream) {
-  return gsp::lanczos_run<float>(n, indptr, indices, data, V3, j0, j1, cap, seed, scal_dev,
+int gsp_lanczos_f32(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                    const float* data, float* V3, int j0, int j1, int cap, uint64_t seed,
+                    double* scal_dev, void* stream) {
+  return gsp::lanczos_run<float>(n, nnz, indptr, indices, data, V3, j0, j1, cap, seed, scal_dev,
                                  gsp::as_stream(stream));
 }
-int gsp_lanczos_f64(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
-                    double* V3, int j0, int j1, int cap, uint64_t seed, double* scal_dev,
-                    void* stream) {
-  return gsp::lanczos_run<double>(n, indptr, indices, data, V3, j0, j1, cap, seed, scal_dev,
+int gsp_lanczos_f64(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                    const double* data, double* V3, int j0, int j1, int cap, uint64_t seed,
+                    double* scal_dev, void* stream) {
+  return gsp::lanczos_run<double>(n, nnz, indptr, indices, data, V3, j0, j1, cap, seed, scal_dev,
                                   gsp::as_stream(stream));
+}
+// y = A x for one vector: scipy's csr_matvec (graph.py:911-917 through ARPACK, graph.py:955)
+int gsp_spmv_f32(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                 const float* data, const float* x, float* y, void* stream) {
+  if (n <= 0) return GSP_OK;
+  return gsp::spmv_launch<float>(n, nnz, indptr, indices, data, x, y, nullptr, 0, nullptr, nullptr,
+                                 nullptr, gsp::as_stream(stream));
+}
+int gsp_spmv_f64(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                 const double* data, const double* x, double* y, void* stream) {
+  if (n <= 0) return GSP_OK;
+  return gsp::spmv_launch<double>(n, nnz, indptr, indices, data, x, y, nullptr, 0, nullptr,
+                                  nullptr, nullptr, gsp::as_stream(stream));
 }
 }

@@ -166,6 +166,7 @@ class PartitionedCheby:
         self.in_splits = [int(v) for v in plan.send_counts]
         self.out_splits = [int(v) for v in plan.recv_counts]
         self._tile_plans = {}
+        self._modes = {}
         self.bytes_sent_per_step = 0
 
     # ------------------------------------------------------------------ pieces
@@ -180,6 +181,38 @@ class PartitionedCheby:
         dist.all_to_all_single(buf[p.n_local:], send, output_split_sizes=self.out_splits,
                                input_split_sizes=self.in_splits, group=self.group)
 
+    def _exchange_mode(self, nsig):
+        """'p2p' or 'nccl' for this signal width -- the SAME answer on every rank.
+
+        A rank-local choice deadlocks near the threshold (one rank enters the peer-window
+        set-up, its neighbour the all-to-all), so the inputs of the decision are reduced over
+        the group once per width: the largest halo of any rank decides the size rule, and
+        p2p is used only if every rank reports that its neighbours are peer-reachable
+        (same host, cudaDeviceCanAccessPeer); otherwise everybody falls back to NCCL.
+        """
+        import torch
+        import torch.distributed as dist
+        if nsig in self._modes:
+            return self._modes[nsig]
+        p = self.plan
+        item = torch.empty((), dtype=self.dtype).element_size()
+        halo_bytes = p.n_halo * nsig * item
+        if not self.backend.has_streams or p.parts == 1:
+            mode = self.exchange or "nccl"
+        else:
+            ok = 1 if self.backend.peers_reachable(self) else 0
+            t = torch.tensor([halo_bytes, -ok], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            max_halo, all_ok = int(t[0].item()), int(t[1].item()) == -1
+            if self.exchange == "nccl" or not all_ok:
+                mode = "nccl"
+            elif self.exchange == "p2p":
+                mode = "p2p"
+            else:
+                mode = "p2p" if max_halo < self.overlap_min_bytes else "nccl"
+        self._modes[nsig] = mode
+        return mode
+
     def _tile_plan(self, nsig, nscales):
         key = (nsig, nscales)
         if key not in self._tile_plans:
@@ -187,11 +220,15 @@ class PartitionedCheby:
         return self._tile_plans[key]
 
     # ---------------------------------------------------------------- operator
-    def cheby_op(self, lmax, c, x, local_order=False):
+    def cheby_op(self, lmax, c, x, local_order=False, clenshaw=None):
         """r = cheby_op(L, c, x) restricted to this rank's rows.
 
         x : (n_local, nsig) tensor on ``self.device`` (original local row order
             unless ``local_order``); returns (nscales, n_local, nsig) in the same order.
+        clenshaw : single-filter calls on the peer-memory path default to Clenshaw's backward
+            recurrence (one pass less over the block per order, same value, different
+            rounding -- as on one GPU); ``False`` keeps the reference's operation order, which
+            is bit-identical to the single-GPU forward recurrence.
         """
         import torch
         p = self.plan
@@ -208,13 +245,10 @@ class PartitionedCheby:
         # wins (7.58 vs 7.89 ms on 2 GPUs).  Huge halos (SBM: 588 MB per step): one packed
         # NCCL transfer overlapped with the interior rows beats 128-byte peer stores
         # (95.7 vs 109.2 ms).  Measured on 2 x B200, profiles/r1_bench_*n2*.json.
-        halo_bytes = p.n_halo * nsig * torch.empty((), dtype=self.dtype).element_size()
-        mode = self.exchange
-        if mode is None:
-            mode = "p2p" if (self.backend.has_streams and p.parts > 1 and
-                             halo_bytes < self.overlap_min_bytes) else "nccl"
+        mode = self._exchange_mode(nsig)
         if mode == "p2p":
-            return self._cheby_op_p2p(lmax, c, x, local_order)
+            return self._cheby_op_p2p(lmax, c, x, local_order,
+                                      True if clenshaw is None else clenshaw)
         bufs = [torch.empty((ext, nsig), dtype=self.dtype, device=self.device) for _ in range(2)]
         xin = x.to(self.dtype)
         bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
@@ -252,6 +286,17 @@ class PartitionedCheby:
         out = torch.empty_like(r)
         out[:, self.perm] = r
         return out
+
+    def filter_pinned(self, lmax, c, xh, clenshaw=None):
+        """``cheby_op`` for a pinned HOST block (n_local, nsig) in the original row order: column
+        chunks are uploaded / filtered / downloaded as a three-stream pipeline
+        (filters/pipeline.py).  Returns a pinned host tensor (nscales, n_local, nsig)."""
+        from .filters import pipeline
+        c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+        p = self.plan          # the chunk width is derived from rank-independent sizes
+        width = pipeline.chunk_width(p.n_global // p.parts, int(xh.shape[1]), xh.element_size())
+        return pipeline.run_pinned(lambda xc: self.cheby_op(lmax, c, xc, clenshaw=clenshaw),
+                                   self.device, self.dtype, xh, c.shape[0], width=width)
 
     # ------------------------------------------------------------------- lmax
     def spmv(self, v):
@@ -326,53 +371,35 @@ class PartitionedCheby:
             return 1.01 * theta
         raise ValueError("The Lanczos method did not converge. Try to use bounds.")
 
-    def _cheby_op_p2p(self, lmax, c, x, local_order):
-        """Same recurrence; the halo travels by peer stores + flags (see PeerWindow)."""
+    def _cheby_op_p2p(self, lmax, c, x, local_order, clenshaw=False):
+        """The whole call is ONE C entry point, ``gsp_cheby_op_dist_*`` (csrc/dist.cu): entry
+        barrier, halo of T_0, K steps with the exchange fused into the step kernel (float32 +
+        tile plan; wait / step / push kernels otherwise).  Python only owns the plan."""
+        import ctypes
         import torch
         p = self.plan
-        c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+        c = np.ascontiguousarray(np.atleast_2d(np.asarray(c, dtype=np.float64)))
         nscales, M = c.shape
         nsig = int(x.shape[1])
         n = p.n_local
         if nsig not in self._windows:
             self._windows[nsig] = PeerWindow(self, nsig)
         win = self._windows[nsig]
-        bufs = win.bufs
-        base = self._seq
-        self._seq = base + M + 2
-        # entry barrier: nobody may write into a neighbour that is still in its previous call
-        win.signal(base + 1)
-        win.wait(base + 1)
         xin = x.to(self.dtype)
-        bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
-        win.push(0, base + 2)                                # halo of T_0
+        if not local_order:
+            xin = xin.index_select(0, self.perm)
+        xin = xin.contiguous()
+        use_clenshaw = bool(clenshaw) and nscales == 1 and M >= 3
         r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
-        plan = self._tile_plan(nsig, nscales)
-        be = self.backend
-        # Fused form: the step kernel itself waits for the halo of T_{k-1}, stores the
-        # boundary rows of T_k into the neighbours from its epilogue (boundary tiles run
-        # first) and publishes the step -- no pack kernel, no collective, no extra launch.
-        fused = (self.fuse_halo and plan is not None and self.dtype == torch.float32 and
-                 nscales <= 16 and win.n_push_rows <= (n // plan.rows_per_tile) * plan.rows_per_tile)
-        cur, old = 0, 1
-        for k in range(1, M):
-            first = k == 1
-            ck = np.ascontiguousarray(c[:, k])
-            c0 = np.ascontiguousarray(c[:, 0])
-            coef = (2.0 / lmax, -1.0, 0.0) if first else (4.0 / lmax, -2.0, -1.0)
-            x_cur, x_new = bufs[cur], bufs[old]
-            if fused:
-                halo = win.fusion(old, base + 1 + k, base + 2 + k, push=k < M - 1)
-                be.step_halo(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
-                             halo)
-            else:
-                win.wait(base + 1 + k)                       # halo of T_{k-1} has landed
-                be.step(self, first, x_cur, x_new, x_new, r, nsig, nscales, ck, c0, coef, plan,
-                        rows=(0, n))
-                if k < M - 1:
-                    win.push(old, base + 2 + k)              # halo of T_k
-            cur, old = old, cur
-        self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * bufs[0].element_size()
+        plan = self._tile_plan(nsig, nscales) if self.fuse_halo else None
+        seq = ctypes.c_uint64(self._seq)
+        with torch.cuda.device(self.device):
+            nat.call("gsp_cheby_op_dist_" + nat.suffix(self.dtype), win.dist_plan, plan,
+                     nat.f64(lmax), c, nat.i32(nscales), nat.i32(M), xin, nat.i64(nsig), r,
+                     nat.i32(1 if use_clenshaw else 0), ctypes.byref(seq),
+                     nat.stream_ptr(self.device))
+        self._seq = int(seq.value)
+        self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * xin.element_size()
         if local_order:
             return r
         out = torch.empty_like(r)
@@ -383,9 +410,10 @@ class PartitionedCheby:
 class PeerWindow:
     """State buffers + flags of one rank for one signal width, IPC-mapped by its neighbours.
 
-    One cudaMalloc'ed block: buf0 | buf1 | flags[P] (uint64) | push counter.  ``push``
+    One cudaMalloc'ed block: buf0 | buf1 | buf2 | flags[P] (uint64) | push counters.  ``push``
     stores this rank's boundary rows into the neighbours' halo rows and publishes a
-    sequence number; ``wait`` stalls the stream until the neighbours published it.
+    sequence number; ``wait`` stalls the stream until the neighbours published it (both live
+    in the library: csrc/halo.cu, csrc/dist.cu -- this class only owns the memory and the tables).
     """
 
     def __init__(self, op, nsig):
@@ -396,7 +424,8 @@ class PeerWindow:
         item = torch.empty((), dtype=op.dtype).element_size()
         ext = p.n_local + p.n_halo
         self.buf_bytes = ((ext * nsig * item + 255) // 256) * 256
-        flag_off = 2 * self.buf_bytes
+        self.n_bufs = 3                       # the Clenshaw form keeps x, b_{k+1} and b_{k+2}
+        flag_off = self.n_bufs * self.buf_bytes
         total = flag_off + 8 * p.parts + 256
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
@@ -404,7 +433,7 @@ class PeerWindow:
             nat.call("gsp_ipc_alloc", ctypes.c_size_t(total), ctypes.byref(ptr), handle)
         self.base = int(ptr.value)
         self.bufs = [_wrap(self.base + b * self.buf_bytes, (ext, nsig), op.dtype, op.device)
-                     for b in range(2)]
+                     for b in range(self.n_bufs)]
         self.flags_ptr = self.base + flag_off
         self.counter_ptr = self.flags_ptr + 8 * p.parts
         # everybody learns everybody's handle, block size and halo layout
@@ -436,13 +465,13 @@ class PeerWindow:
         self.dst_peer = cat(dst_peer, np.int32)
         self.dst_row = cat(dst_row, np.int64)
         self.src_row = op.send_idx
-        base_tab = np.zeros((2, p.parts), dtype=np.int64)
+        base_tab = np.zeros((self.n_bufs, p.parts), dtype=np.int64)
         for q, qbase in self.opened.items():
-            for b in range(2):
+            for b in range(self.n_bufs):
                 base_tab[b, q] = qbase + b * info[q][3]
         self.peer_base = torch.from_numpy(base_tab).to(dev)                  # pointers as int64
-        flag_tab = np.array([self.opened[q] + 2 * info[q][3] + 8 * p.rank for q in self.neighbors],
-                            dtype=np.int64)
+        flag_tab = np.array([self.opened[q] + self.n_bufs * info[q][3] + 8 * p.rank
+                             for q in self.neighbors], dtype=np.int64)
         self.peer_flags = torch.from_numpy(flag_tab).to(dev)
         self.neighbor_ids = torch.from_numpy(np.asarray(self.neighbors, dtype=np.int32)).to(dev)
         # the same send list as a CSR over the local rows, for the fused epilogue push
@@ -455,57 +484,28 @@ class PeerWindow:
         self.push_peer = self.dst_peer[torch.from_numpy(order).to(dev)].contiguous()
         self.push_row = self.dst_row[torch.from_numpy(order).to(dev)].contiguous()
         self.fused_counter_ptr = self.counter_ptr + 8
+        d = nat.DistPlan()
+        d.n_local, d.n_halo, d.nnz = p.n_local, p.n_halo, p.nnz
+        d.indptr, d.indices, d.data = op.indptr.data_ptr(), op.indices.data_ptr(), op.data.data_ptr()
+        for b in range(self.n_bufs):
+            d.buf[b] = self.bufs[b].data_ptr()
+            d.peer_base[b] = self.peer_base[b].data_ptr()
+        d.peer_flags = self.peer_flags.data_ptr()
+        d.flags = self.flags_ptr
+        d.neighbor_ids = self.neighbor_ids.data_ptr()
+        d.n_neighbors = len(self.neighbors)
+        d.push_counter, d.fused_counter = self.counter_ptr, self.fused_counter_ptr
+        d.n_send = int(self.src_row.numel())
+        d.src_row, d.dst_peer, d.dst_row = (self.src_row.data_ptr(), self.dst_peer.data_ptr(),
+                                            self.dst_row.data_ptr())
+        d.n_push_rows = self.n_push_rows
+        d.push_ptr, d.push_peer, d.push_row = (self.push_ptr.data_ptr(), self.push_peer.data_ptr(),
+                                               self.push_row.data_ptr())
+        d.n_boundary_rows = p.n_true_boundary
+        self.dist_plan = d
         torch.cuda.synchronize(dev)
-        dist.barrier(group=op.group)
-
-    def push(self, b, value):
-        """Store my boundary rows of buffer b into the neighbours' buffer b; publish value."""
-        import ctypes
-        torch = nat.require_cuda()
-        op = self.op
-        with torch.cuda.device(op.device):
-            nat.call("gsp_halo_push_" + nat.suffix(op.dtype), nat.i64(self.src_row.numel()),
-                     self.src_row, self.dst_peer, self.dst_row, self.bufs[b],
-                     ctypes.c_void_p(self.peer_base[b].data_ptr()), nat.i64(self.nsig),
-                     self.peer_flags, nat.i32(len(self.neighbors)), nat.u64(value),
-                     ctypes.c_void_p(self.counter_ptr), nat.stream_ptr(op.device))
-
-    def fusion(self, b, wait_value, publish_value, push):
-        """The ``gsp_halo_fusion`` block of one step whose x_new is buffer b."""
-        h = nat.HaloFusion()
-        h.n_push_rows = self.n_push_rows if push else 0
-        h.push_ptr = self.push_ptr.data_ptr()
-        h.push_peer = self.push_peer.data_ptr()
-        h.push_row = self.push_row.data_ptr()
-        h.peer_base = self.peer_base[b].data_ptr()
-        h.peer_flags = self.peer_flags.data_ptr()
-        h.push_counter = self.fused_counter_ptr
-        h.wait_flags = self.flags_ptr
-        h.wait_ids = self.neighbor_ids.data_ptr()
-        h.publish_value = publish_value
-        h.wait_value = wait_value
-        h.n_neighbors = len(self.neighbors)
-        h.n_wait = len(self.neighbors)
-        return h
-
-    def signal(self, value):
-        """Publish value without moving data (entry barrier of a call)."""
-        import ctypes
-        torch = nat.require_cuda()
-        op = self.op
-        with torch.cuda.device(op.device):
-            nat.call("gsp_halo_push_" + nat.suffix(op.dtype), nat.i64(0), self.src_row,
-                     self.dst_peer, self.dst_row, self.bufs[0],
-                     ctypes.c_void_p(self.peer_base[0].data_ptr()), nat.i64(self.nsig),
-                     self.peer_flags, nat.i32(len(self.neighbors)), nat.u64(value),
-                     ctypes.c_void_p(self.counter_ptr), nat.stream_ptr(op.device))
-
-    def wait(self, value):
-        import ctypes
-        torch = nat.require_cuda()
-        with torch.cuda.device(self.op.device):
-            nat.call("gsp_halo_wait", ctypes.c_void_p(self.flags_ptr), self.neighbor_ids,
-                     nat.i32(len(self.neighbors)), nat.u64(value), nat.stream_ptr(self.op.device))
+        if p.parts > 1:
+            dist.barrier(group=op.group)
 
     def close(self):
         import ctypes
@@ -542,6 +542,25 @@ class _CudaBackend:
                                    else "cuda:%d" % torch.cuda.current_device())
         self.comm_stream = torch.cuda.Stream(device=self.device)
         self._evt = None
+
+    def peers_reachable(self, op):
+        """True if every neighbour of this rank is on this host and peer-mappable."""
+        import socket
+        import torch.distributed as dist
+        torch = nat.require_cuda()
+        p = op.plan
+        info = [None] * p.parts
+        dist.all_gather_object(info, (socket.gethostname(), self.device.index), group=op.group)
+        me = info[p.rank]
+        for q in range(p.parts):
+            if q == p.rank or not (p.send_counts[q] > 0 or p.recv_counts[q] > 0):
+                continue
+            host, dev = info[q]
+            if host != me[0]:
+                return False
+            if dev != me[1] and not torch.cuda.can_device_access_peer(me[1], dev):
+                return False
+        return True
 
     def tile_plan(self, op, nsig, nscales):
         torch = nat.require_cuda()
@@ -582,16 +601,6 @@ class _CudaBackend:
             nat.call("gsp_spmm_" + nat.suffix(op.dtype), nat.i64(op.plan.n_local), op.indptr,
                      op.indices, op.data, x_ext, nat.i64(width), y, nat.stream_ptr(self.device))
         return y
-
-    def step_halo(self, op, first, x_cur, x_old, x_new, r, nsig, nscales, ck, c0, coef, plan, halo):
-        torch = nat.require_cuda()
-        with torch.cuda.device(self.device):
-            nat.call("gsp_cheby_step_halo_f32", nat.i32(1 if first else 0),
-                     nat.i64(op.plan.n_local), nat.i64(op.plan.nnz), op.indptr, op.indices,
-                     op.data, x_cur, None if first else x_old, x_new, r,
-                     nat.i64(op.plan.n_local), nat.i64(nsig), nat.i32(nscales), ck, c0,
-                     nat.f64(coef[0]), nat.f64(coef[1]), nat.f64(coef[2]), plan, halo,
-                     nat.stream_ptr(self.device))
 
     def fork_exchange(self, fn):
         """Run the pack + all-to-all on the side stream, after what is queued so far."""

@@ -50,6 +50,13 @@ def _as_device_block(G, signal):
     return x, one_d, kind
 
 
+def _is_pinned_block(s, L):
+    """A contiguous page-locked host tensor of the engine's dtype, big enough to pipeline."""
+    torch = nat.require_cuda()
+    return (torch.is_tensor(s) and not s.is_cuda and s.dim() == 2 and s.dtype == L.dtype
+            and s.is_contiguous() and s.is_pinned() and s.numel() > 0)
+
+
 def _leave_device(t, kind):
     torch = nat.require_cuda()
     if kind == "cuda":
@@ -82,8 +89,11 @@ def _laplacian_on_device(G):
     return cached[1]
 
 
-def cheby_op_device(L, lmax, c, x):
-    """Device-to-device core: x (N, nsig) tensor -> r (Nscales, N, nsig) tensor."""
+def cheby_op_device(L, lmax, c, x, out=None, work=None):
+    """Device-to-device core: x (N, nsig) tensor -> r (Nscales, N, nsig) tensor.
+
+    ``out`` / ``work`` ((Nscales, N, nsig) and (2, N, nsig), contiguous) may be given by callers
+    that keep their buffers (the column-chunk pipeline of host signals)."""
     torch = nat.require_cuda()
     c = np.atleast_2d(np.asarray(c, dtype=np.float64))
     nscales, M = c.shape
@@ -91,8 +101,9 @@ def cheby_op_device(L, lmax, c, x):
         raise TypeError("The coefficients have an invalid shape")
     n, nsig = x.shape
     c = np.ascontiguousarray(c)
-    r = torch.empty((nscales, n, nsig), dtype=L.dtype, device=L.device)
-    work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
+    r = out if out is not None else torch.empty((nscales, n, nsig), dtype=L.dtype, device=L.device)
+    if work is None:
+        work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
     plan = L.tile_plan(nsig, nscales)
     with torch.cuda.device(L.device):
         nat.call("gsp_cheby_op_" + nat.suffix(L.dtype), nat.i64(n), nat.i64(L.nnz), L.indptr,
@@ -101,7 +112,7 @@ def cheby_op_device(L, lmax, c, x):
     return r
 
 
-def cheby_clenshaw_device(L, lmax, c, sources):
+def cheby_clenshaw_device(L, lmax, c, sources, out=None, work=None):
     """sum_i p_i(L) s_i by ONE backward (Clenshaw) recurrence, device to device.
 
     ``sources``: (nsrc, N, nsig) tensor (or (N, nsig) for a single filter), ``c``:
@@ -124,8 +135,10 @@ def cheby_clenshaw_device(L, lmax, c, sources):
     if nsrc > 16:
         raise ValueError("at most 16 source blocks per call")
     sources = sources.contiguous()
-    out = torch.empty((n, nsig), dtype=L.dtype, device=L.device)
-    work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
+    if out is None:
+        out = torch.empty((n, nsig), dtype=L.dtype, device=L.device)
+    if work is None:
+        work = torch.empty((2, n, nsig), dtype=L.dtype, device=L.device)
     plan = L.tile_plan(nsig, nsrc)
     with torch.cuda.device(L.device):
         nat.call("gsp_cheby_clenshaw_" + nat.suffix(L.dtype), nat.i64(n), nat.i64(L.nnz),
@@ -144,8 +157,9 @@ def cheby_op(G, c, signal, **kwargs):
     filter-major row blocks.  ``M < 2`` raises TypeError.  NumPy in -> NumPy
     out, CUDA tensor in -> CUDA tensor out.  The arithmetic type is the
     graph's (float32 by default; the reference always computes in float64).
-    ``clenshaw=True`` (single filter only) evaluates the same polynomial by Clenshaw's
-    backward recurrence, which needs one pass less over the signal block per order.
+    A single filter is evaluated by Clenshaw's backward recurrence (one pass less over the
+    signal block per order, same value, different rounding); ``clenshaw=False`` keeps the
+    reference's forward recurrence and operation order.
     """
     if not isinstance(c, np.ndarray):
         c = np.array(c)
@@ -157,9 +171,12 @@ def cheby_op(G, c, signal, **kwargs):
     if x.shape[0] != G.N:
         raise ValueError("First dimension must be the number of vertices "
                          "G.N = {}, got {}.".format(G.N, tuple(x.shape)))
-    if kwargs.get("clenshaw", False):
-        if c.shape[0] != 1:
-            raise ValueError("clenshaw=True evaluates a single filter")
+    clenshaw = kwargs.get("clenshaw", None)
+    if clenshaw and c.shape[0] != 1:
+        raise ValueError("clenshaw=True evaluates a single filter")
+    if clenshaw is None:
+        clenshaw = c.shape[0] == 1
+    if clenshaw:
         r = cheby_clenshaw_device(L, G.lmax, c[0], x)
     else:
         r = cheby_op_device(L, G.lmax, c, x)

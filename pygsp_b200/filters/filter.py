@@ -39,6 +39,10 @@ class Filter:
         # forward recurrences (Nf * K SpMMs); same value, different rounding.  Set to
         # False to reproduce the reference's operation order.
         self.fused_synthesis = True
+        # a single filter is evaluated by Clenshaw's backward recurrence: 4 instead of 5
+        # passes over the signal block per order (no accumulator block), same value,
+        # different rounding.  False = the reference's forward recurrence and operation order.
+        self.clenshaw = True
 
     def _get_extra_repr(self):
         return dict()
@@ -115,8 +119,17 @@ class Filter:
         view = approximations._GraphView(L)
 
         if n_features_in == 1:                                   # analysis
-            x, _, kind = approximations._as_device_block(view, s.reshape(N, n_signals))
-            r = approximations.cheby_op_device(L, self.G.lmax, c, x)      # (Nf, N, nsig)
+            flat = s.reshape(N, n_signals)
+            if approximations._is_pinned_block(flat, L):
+                # page-locked host block: column chunks, transfers overlapped with the recurrence
+                from . import pipeline
+                r = pipeline.filter_pinned(L, self.G.lmax, c, flat, clenshaw=self.clenshaw)
+                return r.permute(1, 2, 0).squeeze()
+            x, _, kind = approximations._as_device_block(view, flat)
+            if self.clenshaw and c.shape[0] == 1:
+                r = approximations.cheby_clenshaw_device(L, self.G.lmax, c, x)[None]
+            else:
+                r = approximations.cheby_op_device(L, self.G.lmax, c, x)  # (Nf, N, nsig)
             out = r.permute(1, 2, 0)                                      # (N, nsig, Nf)
         else:                                                    # synthesis
             x, _, kind = approximations._as_device_block(view, s.reshape(N, -1))

@@ -1,0 +1,133 @@
+"""Filtering of HOST signal blocks with the PCIe transfers overlapped.
+
+``Filter.filter`` / ``cheby_op`` take and return host arrays in the reference
+(pygsp/filters/filter.py:146-328, approximations.py:58-114).  Uploading the block,
+running the recurrence and downloading the result one after the other makes the two
+transfers longer than the recurrence itself (config 2: 4.7 + 7.9 + 4.7 ms).  The
+recurrence needs all ROWS of its operand before its first step but its COLUMNS are
+independent, so the block is cut into column chunks and three streams run as a
+pipeline:
+
+    upload stream   : chunk j+1  host -> HBM   (strided 2-D copy of a pinned block)
+    compute stream  : chunk j    K fused recurrence steps
+    download stream : chunk j-1  HBM -> host
+
+Only page-locked (pinned) torch tensors take this path -- the copy engines cannot run
+asynchronously on pageable memory; NumPy / pageable inputs use one plain copy each way.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .. import _native as nat
+
+_TILED_WIDTHS = (128, 64, 32, 16, 8)
+_streams = {}
+
+
+def _side_streams(device):
+    torch = nat.require_cuda()
+    key = (device.type, device.index)
+    if key not in _streams:
+        _streams[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _streams[key]
+
+
+def chunk_width(n, nsig, itemsize, nscales=1):
+    """Column-chunk width for an (n, nsig) block: the widest split into >= 2 chunks whose width
+    the tiled kernel supports, provided a chunk still is a sizeable transfer (>= 8 MB) --
+    otherwise the whole block (no pipelining).  GSPB200_E2E_CHUNK overrides (0 = off)."""
+    env = os.environ.get("GSPB200_E2E_CHUNK")
+    if env is not None:
+        w = int(env)
+        return w if (w > 0 and nsig % w == 0) else nsig
+    for w in _TILED_WIDTHS:
+        if w <= nsig // 2 and nsig % w == 0 and n * w * itemsize >= (8 << 20):
+            return w
+    return nsig
+
+
+def _copy2d(dst_ptr, dpitch, src_ptr, spitch, width, height, kind, stream, use_kernel):
+    if use_kernel:
+        nat.call("gsp_stage_cols", ctypes.c_void_p(dst_ptr), ctypes.c_size_t(dpitch),
+                 ctypes.c_void_p(src_ptr), ctypes.c_size_t(spitch), ctypes.c_size_t(width),
+                 ctypes.c_size_t(height), nat.i32(int(os.environ.get("GSPB200_STAGE_BLOCKS", "16"))),
+                 ctypes.c_void_p(stream.cuda_stream))
+    else:
+        nat.call("gsp_copy2d_async", ctypes.c_void_p(dst_ptr), ctypes.c_size_t(dpitch),
+                 ctypes.c_void_p(src_ptr), ctypes.c_size_t(spitch), ctypes.c_size_t(width),
+                 ctypes.c_size_t(height), nat.i32(kind), ctypes.c_void_p(stream.cuda_stream))
+
+
+def run_pinned(compute, device, dtype, xh, nscales, out=None, width=None):
+    """The three-stream pipeline for any column-separable operator.
+
+    ``compute(x_chunk)`` maps an (n, w) device block to an (nscales, n, w) device tensor on the
+    current stream (it may return a fresh tensor per call; references are kept until the
+    downloads have finished).  ``xh``: contiguous pinned host tensor (n, nsig).  Returns the
+    pinned host tensor (nscales, n, nsig), complete on return.  ``width``: chunk width
+    (default: :func:`chunk_width`; callers whose ranks must agree pass it explicitly).
+    """
+    torch = nat.require_cuda()
+    n, nsig = xh.shape
+    item = xh.element_size()
+    if xh.dtype != dtype or not xh.is_contiguous() or not xh.is_pinned():
+        raise ValueError("the pipelined path needs a contiguous pinned host tensor of the engine's dtype")
+    if out is None:
+        out = torch.empty((nscales, n, nsig), dtype=dtype, pin_memory=True)
+    w = width if width else chunk_width(n, nsig, item, nscales)
+    nchunks = nsig // w
+    use_kernel = os.environ.get("GSPB200_STAGE", "dma") == "kernel"
+    with torch.cuda.device(device):
+        main = torch.cuda.current_stream(device)
+        s_in, s_out = _side_streams(device)
+        nbuf = min(2, nchunks)
+        xin = [torch.empty((n, w), dtype=dtype, device=device) for _ in range(nbuf)]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        ev_in = [None] * nchunks
+        ev_comp = [None] * nchunks
+        results = []
+
+        def upload(j):
+            b = j % nbuf
+            if j >= nbuf:                      # the buffer's previous chunk has been consumed
+                s_in.wait_event(ev_comp[j - nbuf])
+            _copy2d(xin[b].data_ptr(), w * item, xh.data_ptr() + j * w * item, nsig * item,
+                    w * item, n, 1, s_in, use_kernel)
+            ev_in[j] = s_in.record_event()
+
+        upload(0)
+        for j in range(nchunks):
+            if j + 1 < nchunks:
+                upload(j + 1)
+            main.wait_event(ev_in[j])
+            res = compute(xin[j % nbuf])
+            results.append(res)
+            ev_comp[j] = main.record_event()
+            s_out.wait_event(ev_comp[j])
+            for i in range(nscales):
+                _copy2d(out[i].data_ptr() + j * w * item, nsig * item, res[i].data_ptr(),
+                        w * item, w * item, n, 2, s_out, use_kernel)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)
+        main.synchronize()                     # a host result must be complete on return
+    return out
+
+
+def filter_pinned(L, lmax, c, xh, clenshaw=True, out=None):
+    """r = cheby_op(L, c, x) for a PINNED host block ``xh`` (N, nsig) of ``L.dtype``.
+
+    Returns a pinned host tensor (Nscales, N, nsig) (``out`` if given), complete when the
+    function returns.  Single-filter banks use the Clenshaw form when ``clenshaw`` (one pass
+    less over the block per order, see ``cheby_clenshaw_device``).
+    """
+    from . import approximations as apx
+    c = np.ascontiguousarray(np.atleast_2d(np.asarray(c, dtype=np.float64)))
+    nscales = c.shape[0]
+    if nscales == 1 and clenshaw:
+        compute = lambda xc: apx.cheby_clenshaw_device(L, lmax, c, xc)[None]
+    else:
+        compute = lambda xc: apx.cheby_op_device(L, lmax, c, xc)
+    return run_pinned(compute, L.device, L.dtype, xh, nscales, out)

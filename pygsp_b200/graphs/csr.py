@@ -85,9 +85,14 @@ class DeviceCSR:
         flat = xt.reshape(xt.shape[0], -1).contiguous()
         y = torch.empty((self.shape[0], flat.shape[1]), dtype=self.dtype, device=self.device)
         with torch.cuda.device(self.device):
-            nat.call("gsp_spmm_" + nat.suffix(self.dtype), nat.i64(self.shape[0]), self.indptr,
-                     self.indices, self.data, flat, nat.i64(flat.shape[1]), y,
-                     nat.stream_ptr(self.device))
+            if flat.shape[1] == 1:                      # one vector: the sub-warp SpMV
+                nat.call("gsp_spmv_" + nat.suffix(self.dtype), nat.i64(self.shape[0]),
+                         nat.i64(self.nnz), self.indptr, self.indices, self.data, flat, y,
+                         nat.stream_ptr(self.device))
+            else:
+                nat.call("gsp_spmm_" + nat.suffix(self.dtype), nat.i64(self.shape[0]),
+                         self.indptr, self.indices, self.data, flat, nat.i64(flat.shape[1]), y,
+                         nat.stream_ptr(self.device))
         y = y.reshape((self.shape[0],) + tuple(xt.shape[1:]))
         return y.cpu().numpy() if host else y
 

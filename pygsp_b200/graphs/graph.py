@@ -357,17 +357,17 @@ class Graph:
             return 0.0
         cap = int(min(n, max_steps))
         V = torch.empty(3 * n, dtype=self.dtype, device=self.device)
-        scal = torch.zeros(2 * cap + 4096, dtype=torch.float64, device=self.device)
+        scal = torch.zeros(2 * cap + 1 + 4096, dtype=torch.float64, device=self.device)
         done = 0
         theta = None
         converged = False
         while done < cap:
             nxt = min(cap, done + (10 if done == 0 else 5))     # ncv = min(N, 10) first
-            self._call("gsp_lanczos", nat.i64(n), L.indptr, L.indices, L.data, V,
+            self._call("gsp_lanczos", nat.i64(n), nat.i64(L.nnz), L.indptr, L.indices, L.data, V,
                        nat.i32(done), nat.i32(nxt), nat.i32(cap), nat.u64(seed), scal)
             done = nxt
             host = scal.cpu().numpy()
-            theta, m, stop, ref_rule = ritz_check(host[:done], host[cap:cap + done], tol,
+            theta, m, stop, ref_rule = ritz_check(host[:done], host[cap + 1:cap + 1 + done], tol,
                                                   self._sfx == "f32", done >= polish_steps)
             self._lanczos_steps = m
             converged = converged or ref_rule

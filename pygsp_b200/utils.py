@@ -56,3 +56,34 @@ def symmetrize(W, method="average"):
         tri = getattr(sparse if sparse.issparse(W) else np, method)(W)
         return symmetrize(tri, "maximum")
     raise ValueError("Unknown symmetrization method {}.".format(method))
+
+
+def bind_to_gpu_numa(device_index=0):
+    """Pin this process (and the host memory it allocates from now on) to the NUMA node of a GPU.
+
+    One process per GPU: the pinned staging buffers of Filter.filter's host path should
+    live on the socket the GPU hangs off, otherwise every transfer crosses the inter-socket
+    link (on an 8-GPU box half of the ranks do by default).  Uses NVML's ideal-CPU mask of
+    the device (matched by UUID, so CUDA_VISIBLE_DEVICES renumbering is harmless) and the
+    first-touch policy.  Returns the number of CPUs in the mask, or 0 when NVML is not usable
+    (nothing is changed then).
+    """
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return 0
+        os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return 0

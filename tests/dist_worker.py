@@ -112,7 +112,7 @@ def main():
     est = op.estimate_lmax()
     assert lam * (1 - 2e-4) <= est / 1.01 <= lam * (1 + 1e-5), (est, lam)
     assert op.estimate_lmax(method="bounds") >= lam
-    r = op.cheby_op(lmax, c, xl).cpu().numpy().astype(np.float64)
+    r = op.cheby_op(lmax, c, xl, clenshaw=False).cpu().numpy().astype(np.float64)
     want = ref[:, lo:hi]
     err = np.abs(r - want).max() / np.abs(ref).max()
     assert err <= tol, (rank, err)
@@ -124,11 +124,25 @@ def main():
         Ld = DeviceCSR.from_scipy(L, dtype, op.device)        # the same float32 values of L
         full = apx.cheby_op_device(Ld, lmax, c, torch.from_numpy(x).to(op.device, dtype))
         for _ in range(3):                                   # repeated calls reuse windows / flags
-            mine = op.cheby_op(lmax, c, xl)
+            mine = op.cheby_op(lmax, c, xl, clenshaw=False)
             assert torch.equal(mine, full[:, lo:hi]), float((mine - full[:, lo:hi]).abs().max())
+        # single filter: the peer-memory path defaults to the Clenshaw form, bit-identical to the
+        # single-GPU Clenshaw evaluation; the NCCL path keeps the forward recurrence
+        xd = torch.from_numpy(x).to(op.device, dtype)
+        c1 = c[:1]
+        fwd1 = apx.cheby_op_device(Ld, lmax, c1, xd)
+        cl1 = apx.cheby_clenshaw_device(Ld, lmax, c1, xd)[None]
+        want1 = cl1 if overlap in ("p2p", "p2p_unfused") else fwd1
+        for _ in range(2):
+            mine1 = op.cheby_op(lmax, c1, xl)
+            assert torch.equal(mine1, want1[:, lo:hi]), float((mine1 - want1[:, lo:hi]).abs().max())
+        assert torch.equal(op.cheby_op(lmax, c1, xl, clenshaw=False), fwd1[:, lo:hi])
+        e1 = float((cl1 - fwd1).abs().max() / fwd1.abs().max())
+        assert e1 <= 2e-5, e1
         x2 = torch.from_numpy(x[:, :32].copy()).to(op.device, dtype)      # another signal width
         full2 = apx.cheby_op_device(Ld, lmax, c, x2)
-        assert torch.equal(op.cheby_op(lmax, c, x2[lo:hi].contiguous()), full2[:, lo:hi])
+        assert torch.equal(op.cheby_op(lmax, c, x2[lo:hi].contiguous(), clenshaw=False),
+                           full2[:, lo:hi])
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok err=%.2e halo=%d boundary=%d/%d" % (rank, err, plan.n_halo, plan.n_true_boundary,

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
         assert required in names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.gsp_abi_version() == 1
+    assert lib.gsp_abi_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -591,3 +591,105 @@ def test_full_size_properties(gsp, sensor1m):
         v = v / v.norm()
     rq = float((v * G.L.dot(v)).sum())
     assert rq <= G.lmax / 1.01 * (1 + 1e-4) and G.lmax <= 1.01 * rq * 1.2
+
+
+# ---------------------------------------------------------- round 2: SpMV, pipeline
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spmv_subwarp_matches_scipy(gsp, dtype):
+    """gsp_spmv_* (sub-warp rows, shuffle reduction) on graphs of very different mean degree."""
+    import torch
+    from scipy import sparse
+    rng = np.random.default_rng(5)
+    mats = [gsp.graphs.Sensor(3000, k=10, seed=1, dtype=dtype).L.to_scipy(),
+            gsp.graphs.Grid2d(37, 41, dtype=dtype).L.to_scipy(),
+            sparse.random(500, 500, 0.3, random_state=3, format="csr", dtype=np.float64),
+            sparse.random(400, 400, 0.004, random_state=4, format="csr", dtype=np.float64),
+            sparse.csr_matrix((7, 7), dtype=np.float64)]
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    for M in mats:
+        M = M.astype(np.float64).tocsr()
+        M.sort_indices()
+        D = gsp.graphs.DeviceCSR.from_scipy(M, tdt, torch.device("cuda"))
+        v = rng.standard_normal(M.shape[1])
+        got = D.dot(v)
+        ref = M.dot(v)
+        assert got.shape == ref.shape
+        scale = max(np.abs(ref).max(), 1e-30)
+        assert np.abs(got - ref).max() / scale <= (2e-6 if dtype == np.float32 else 1e-13)
+
+
+def test_staging_copies_move_column_chunks(gsp):
+    """gsp_copy2d_async and gsp_stage_cols: a strided column chunk host -> device -> host."""
+    import ctypes
+    import torch
+    from pygsp_b200 import _native as nat
+    n, nsig, w = 1000, 64, 16
+    xh = torch.randn(n, nsig).pin_memory()
+    for use_kernel in (False, True):
+        dev = torch.zeros(n, w, device="cuda")
+        back = torch.zeros(n, nsig).pin_memory()
+        st = torch.cuda.current_stream()
+        for j in range(nsig // w):
+            args_in = (ctypes.c_void_p(dev.data_ptr()), ctypes.c_size_t(w * 4),
+                       ctypes.c_void_p(xh.data_ptr() + j * w * 4), ctypes.c_size_t(nsig * 4),
+                       ctypes.c_size_t(w * 4), ctypes.c_size_t(n))
+            args_out = (ctypes.c_void_p(back.data_ptr() + j * w * 4), ctypes.c_size_t(nsig * 4),
+                        ctypes.c_void_p(dev.data_ptr()), ctypes.c_size_t(w * 4),
+                        ctypes.c_size_t(w * 4), ctypes.c_size_t(n))
+            if use_kernel:
+                nat.call("gsp_stage_cols", *args_in, nat.i32(4), ctypes.c_void_p(st.cuda_stream))
+                nat.call("gsp_stage_cols", *args_out, nat.i32(4), ctypes.c_void_p(st.cuda_stream))
+            else:
+                nat.call("gsp_copy2d_async", *args_in, nat.i32(1), ctypes.c_void_p(st.cuda_stream))
+                torch.cuda.synchronize()
+                assert torch.equal(dev.cpu(), xh[:, j * w:(j + 1) * w])
+                nat.call("gsp_copy2d_async", *args_out, nat.i32(2), ctypes.c_void_p(st.cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(back, xh)
+
+
+@pytest.mark.parametrize("stage", ["dma", "kernel"])
+@pytest.mark.parametrize("nf", [1, 3])
+def test_pinned_host_pipeline_equals_device_path(gsp, monkeypatch, stage, nf):
+    """Filter.filter on a pinned host block (column-chunk pipeline, 4 chunks of 16) returns the
+    bits of the device-resident path, for one filter (Clenshaw) and for a bank (forward)."""
+    import torch
+    monkeypatch.setenv("GSPB200_E2E_CHUNK", "16")
+    monkeypatch.setenv("GSPB200_STAGE", stage)
+    G = gsp.graphs.Sensor(30000, k=8, seed=2, order="morton")
+    G.estimate_lmax()
+    g = gsp.filters.Heat(G, scale=[10, 20, 40][:nf]) if nf > 1 else gsp.filters.Heat(G, scale=50)
+    x = torch.randn(G.N, 64, device="cuda")
+    want = g.filter(x, order=20)
+    xh = torch.empty(G.N, 64).pin_memory()
+    xh.copy_(x)
+    for _ in range(2):                       # second call reuses streams / cached blocks
+        got = g.filter(xh, order=20)
+        assert not got.is_cuda and got.shape == want.shape
+        assert torch.equal(got.cuda(), want)
+    # and against the oracle
+    Lo = G.L.to_scipy().astype(np.float64)
+    ref = orc.filter_signal(Lo, G.lmax, orc.heat_kernels(G.lmax, [10, 20, 40][:nf] if nf > 1 else 50),
+                            x[:, :3].double().cpu().numpy(), order=20)
+    assert relerr_cols(got.numpy()[:, :3].reshape(ref.shape), ref) <= F32_TOL
+
+
+def test_clenshaw_is_the_default_for_one_filter(gsp, sensor5k):
+    """One filter: Filter.filter / cheby_op evaluate by Clenshaw's recurrence unless told
+    otherwise; the reference order stays available and both match the oracle."""
+    import torch
+    from pygsp_b200.filters import approximations as apx
+    G, L, _ = sensor5k
+    g = gsp.filters.Heat(G, scale=30)
+    c = np.atleast_2d(gsp.filters.compute_cheby_coeff(g, m=25))
+    x = torch.randn(G.N, 32, device="cuda")
+    y = g.filter(x, order=25)
+    assert torch.equal(y, apx.cheby_clenshaw_device(G.L, G.lmax, c, x))
+    g.clenshaw = False
+    y_ref_order = g.filter(x, order=25)
+    assert torch.equal(y_ref_order, apx.cheby_op_device(G.L, G.lmax, c, x)[0])
+    ref = orc.cheby_op(L, G.lmax, c, x.double().cpu().numpy())
+    assert relerr_cols(y.cpu().numpy(), ref) <= F32_TOL
+    assert relerr_cols(y_ref_order.cpu().numpy(), ref) <= F32_TOL
+    got = apx.cheby_op(G, c[0], x.cpu().numpy())                 # free function, NumPy in / out
+    assert relerr_cols(got, ref) <= F32_TOL
