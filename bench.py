@@ -563,7 +563,8 @@ def run_ours(args):
         run_dev = device_op(apx, G.L, lmax, c)
         run_host = lambda xh: bank.filter(xh, order=order)
     else:
-        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=False)
+        local_order = os.environ.get("GSPB200_BENCH_LOCAL_ORDER") == "1"    # diagnosis only
+        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=local_order)
         run_host = lambda xh: op.filter_pinned(lmax, c, xh)[0]
 
     # ---- device-resident throughput ("value")
@@ -602,7 +603,7 @@ def run_ours(args):
         assert tuple(yh.shape)[:2] == (n, nsig) and not yh.is_cuda
         e2e_err = float((yh.to("cuda") - y_dev[0]).abs().max() / y_dev[0].abs().max())
         from pygsp_b200.filters import pipeline
-        wchunk = pipeline.chunk_width(n_global // world, nsig, 4)
+        chunks = pipeline.chunk_plan(n_global // world, nsig, 4)
         e2e = {"value": n_global * nsig * order * args.steps / t_e2e, "unit": UNIT,
                "h2d_bytes_per_step": 4 * n_global * nsig,
                "d2h_bytes_per_step": 4 * n_global * nsig * wl["nscales"],
@@ -610,9 +611,9 @@ def run_ours(args):
                "api": ("%s.filter(pinned_host_tensor, order=%d)" % (
                    "Heat(G, 50)", order)) if world == 1 else
                       "PartitionedCheby.filter_pinned(pinned host block of the rank's rows)",
-               "pipeline": "%d column chunks of %d signals: upload j+1 / recurrence j / download j-1 "
+               "pipeline": "column chunks of %s signals: upload j+1 / recurrence j / download j-1 "
                            "on three streams (strided 2-D copies by %s)" % (
-                               nsig // wchunk, wchunk,
+                               " | ".join(str(w) for _, w in chunks),
                                "a zero-copy kernel" if os.environ.get("GSPB200_STAGE") == "kernel"
                                else "the copy engines"),
                "max_abs_diff_vs_device_path_rel": e2e_err, "numa_cpus_bound": numa_cpus}
@@ -625,7 +626,7 @@ def run_ours(args):
         # engine's on the rank's rows (same kernels, same summation order: expected 0.0)
         single = device_op(apx, G.L, lmax, c)
         full = single(x_full)
-        mine = run_dev(x)
+        mine = op.cheby_op(lmax, c, x, local_order=False)
         err = float((mine - full[:, lo:lo + n]).abs().max() / full.abs().max())
         parity["parity_rel_err"] = allmax(err)
         parity["parity_bit_identical_on_every_rank"] = allmax(0.0 if torch.equal(

@@ -186,6 +186,25 @@ int gsp_lanczos_f64(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t
  * gsp_gather_rows_* / gsp_scatter_rows_*  dst[i,:] = src[idx[i],:] / dst[idx[i],:] = src[i,:]
  *     (vertex reordering in and out, halo packing).
  */
+/* ----------------------------------------------------------------- solver ---
+ * gsp_cg_*: conjugate gradients for (diag(row_scale) * tau * L + diag(diag)) X = B, a block
+ *   of nsig <= 256 right-hand sides advancing together.  Stands for scipy.sparse.linalg.cg
+ *   on the operator x -> M x + tau L x of pygsp/learning.py:326-337 (regression_tikhonov,
+ *   one solve per column there) and, with row_scale = 1 - M, diag = 0, for the constrained
+ *   problem of learning.py:350-365 restricted to the unlabelled vertices.  row_scale / diag
+ *   are length-n vectors or NULL (= 1 / = 0).  Runs iterations [it0, it1) (it0 == 0 starts
+ *   from X = 0); X, R, P, Q are (n, nsig) state blocks owned by the caller; scal_dev holds
+ *   (cap + 1 + 2048) * nsig doubles, its first (cap + 1) x nsig entries are the history of
+ *   the squared residual norms per column, which the host reads to test convergence. */
+#define GSPB200_DECLARE_CG_API(SUF, T)                                                           \
+  int gsp_cg_##SUF(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,       \
+                   const T* data, double tau, const T* row_scale, const T* diag, const T* B,     \
+                   T* X, T* R, T* P, T* Q, int64_t nsig, int it0, int it1, int cap,              \
+                   double* scal_dev, void* stream);
+
+GSPB200_DECLARE_CG_API(f32, float)
+GSPB200_DECLARE_CG_API(f64, double)
+
 /* ------------------------------------------------- host <-> device staging ---
  * Filter.filter() takes and returns host arrays (filter.py:146-328).  To overlap the PCIe
  * transfers with the recurrence the signal block is processed in COLUMN chunks; a chunk of a
@@ -248,8 +267,10 @@ int gsp_halo_wait(const uint64_t* flags, const int32_t* neighbor_ids, int n_neig
  *   src_row/dst_peer/dst_row (n_send entries): the rows to push as a flat list;
  *   push_ptr/push_peer/push_row: the same list as a CSR over local rows [0, n_push_rows)
  *   push_counter / fused_counter: zero-initialised device counters owned by the caller
- *   x : (n_local, nsig) input in LOCAL row order (NULL: already in buf[0]);
- *   r : (nscales, n_local, nsig) output, local row order;
+ *   x : (n_local, nsig) input (NULL: already in buf[0], local order);
+ *   r : (nscales, n_local, nsig) output; x and r are in the CALLER's row order when
+ *       plan->perm is given (the gather into local order replaces the copy into buf[0]; the
+ *       Clenshaw form stores its last step straight to the caller's rows), else local order;
  *   clenshaw != 0 and nscales == 1: backward (Clenshaw) recurrence, one pass less per order;
  *   seq_host : the rank's sequence counter (starts at 0, advanced by m + 2 per call; all
  *              ranks must make the same calls in the same order).
@@ -277,6 +298,7 @@ typedef struct gsp_dist_plan {
   const int32_t* push_peer;
   const int64_t* push_row;
   int64_t n_boundary_rows;
+  const int64_t* perm;               /* local row i = row perm[i] of the caller's blocks; NULL: identity */
 } gsp_dist_plan;
 
 int gsp_cheby_op_dist_f32(const gsp_dist_plan* plan_host, const gsp_tile_plan* tile_host,

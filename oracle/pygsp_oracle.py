@@ -353,3 +353,94 @@ def filter_signal(L, lmax, kernels, s, order=30):
             out += cheby_op(L, lmax, c[i], s[:, :, i])
         out = out[:, :, None]
     return out.squeeze()
+
+
+# --------------------------------------------------------------------------- callers
+# reduction.interpolate / pyramid_analysis / pyramid_synthesis (direct
+# branch) and learning.regression_tikhonov.  Restated on top of the oracle's own filter.
+def kron_reduction(L, ind):
+    """Schur complement of L onto the vertices ``ind`` (reduction.py:352-366, matrix branch)."""
+    from scipy.sparse import linalg
+    L = sparse.csr_matrix(L)
+    n = L.shape[0]
+    ind = np.asarray(ind)
+    comp = np.setdiff1d(np.arange(n, dtype=int), ind)
+    L_red = L[np.ix_(ind, ind)]
+    L_in_out = L[np.ix_(ind, comp)]
+    L_out_in = L[np.ix_(comp, ind)].tocsc()
+    L_comp = L[np.ix_(comp, comp)].tocsc()
+    Lnew = L_red - L_in_out.dot(linalg.spsolve(L_comp, L_out_in))
+    if np.abs(Lnew - Lnew.T).sum() < np.spacing(1) * np.abs(Lnew).sum():
+        Lnew = (Lnew + Lnew.T) / 2.0
+    return sparse.csr_matrix(Lnew)
+
+
+def _legacy_analysis(L, lmax, kernel, s, order):
+    """reduction.py:26-31 ``_analysis`` for a one-filter bank and an (N, Nv) signal block;
+    column j of the result is the filtered column j (the reference's reshape keeps that
+    layout only for Nv == 1 -- see tests/golden/make_golden_r2.py)."""
+    s = np.asarray(s, dtype=np.float64)
+    cols = s.reshape(s.shape[0], -1)
+    out = filter_signal(L, lmax, [kernel], cols, order=order)
+    return np.asarray(out).reshape(cols.shape)
+
+
+def interpolate(L, lmax, f_subsampled, keep_inds, order=100, reg_eps=0.005, K_reg=None):
+    """reduction.py:150-193: alpha = K_reg f; zero-fill; Green kernel 1/(eps + x) filter."""
+    n = L.shape[0]
+    if K_reg is None:
+        K_reg = kron_reduction(L + reg_eps * sparse.eye(n), keep_inds)
+    f_subsampled = np.asarray(f_subsampled, dtype=np.float64)
+    sub = f_subsampled.reshape(f_subsampled.shape[0], -1)
+    full = np.zeros((n, sub.shape[1]))
+    full[np.asarray(keep_inds)] = K_reg.dot(sub)
+    return _legacy_analysis(L, lmax, lambda x: 1.0 / (reg_eps + x), full, order)
+
+
+def pyramid_analysis(Ls, lmaxs, idxs, f, h, order=30, reg_eps=0.005, K_regs=None):
+    """reduction.py:384-449.  Ls / lmaxs: Laplacian and lmax per level (levels + 1 of them),
+    idxs[i] = vertices of level i kept at level i + 1, h: one kernel for all levels."""
+    levels = len(Ls) - 1
+    f = np.asarray(f, dtype=np.float64)
+    ca, pe = [f.reshape(f.shape[0], -1)], []
+    for i in range(levels):
+        s_low = _legacy_analysis(Ls[i], lmaxs[i], h, ca[i], order)
+        ca.append(s_low[idxs[i]])
+        s_pred = interpolate(Ls[i], lmaxs[i], ca[i + 1], idxs[i], order=order, reg_eps=reg_eps,
+                             K_reg=None if K_regs is None else K_regs[i])
+        pe.append(ca[i] - s_pred)
+    return ca, pe
+
+
+def pyramid_synthesis(Ls, lmaxs, idxs, cap, pe, order=30, reg_eps=0.005, K_regs=None):
+    """reduction.py:504-514, direct (not least-squares) branch."""
+    levels = len(Ls) - 1
+    ca = [np.asarray(cap, dtype=np.float64)]
+    for i in range(levels):
+        lv = levels - i - 1
+        s_pred = interpolate(Ls[lv], lmaxs[lv], ca[i], idxs[lv], order=order, reg_eps=reg_eps,
+                             K_reg=None if K_regs is None else K_regs[lv])
+        ca.append(s_pred + pe[lv])
+    return ca[levels], ca
+
+
+def regression_tikhonov(L, y, M, tau=0):
+    """learning.py:255-365 solved EXACTLY (sparse direct): argmin |Mx - y|^2 + tau x'Lx for
+    tau > 0 (the reference runs scipy CG to rtol 1e-5 on the same system), and the harmonic
+    extension L_uu x_u = -L_ul y_l for tau = 0 (:350-365)."""
+    from scipy.sparse import linalg
+    L = sparse.csr_matrix(L, dtype=np.float64)
+    M = np.asarray(M, dtype=bool)
+    y = np.array(y, dtype=np.float64)
+    if tau > 0:
+        y[~M] = 0
+        A = (sparse.diags(M.astype(np.float64)) + tau * L).tocsc()
+        return linalg.spsolve(A, y) if y.ndim == 1 else linalg.splu(A).solve(y)
+    if M.size != L.shape[0]:
+        raise ValueError("M should be of size [G.n_vertices,]")
+    Luu = L[~M, :][:, ~M].tocsc()
+    Wul = -L[~M, :][:, M]
+    sol = y.copy()
+    rhs = Wul.dot(y[M])
+    sol[~M] = linalg.spsolve(Luu, rhs) if rhs.ndim == 1 else linalg.splu(Luu).solve(rhs)
+    return sol

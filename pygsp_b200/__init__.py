@@ -9,6 +9,8 @@ from . import _native  # noqa: F401
 from . import utils  # noqa: F401
 from . import graphs  # noqa: F401
 from . import filters  # noqa: F401
+from . import reduction  # noqa: F401
+from . import learning  # noqa: F401
 
 __version__ = "0.1.0"
 

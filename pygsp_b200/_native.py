@@ -56,7 +56,8 @@ class DistPlan(ctypes.Structure):
                 ("src_row", ctypes.c_void_p), ("dst_peer", ctypes.c_void_p),
                 ("dst_row", ctypes.c_void_p), ("n_push_rows", ctypes.c_int64),
                 ("push_ptr", ctypes.c_void_p), ("push_peer", ctypes.c_void_p),
-                ("push_row", ctypes.c_void_p), ("n_boundary_rows", ctypes.c_int64)]
+                ("push_row", ctypes.c_void_p), ("n_boundary_rows", ctypes.c_int64),
+                ("perm", ctypes.c_void_p)]
 
 
 def header_symbols():

@@ -32,7 +32,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
                          int64_t* rows_done, cudaStream_t st, bool add_source = false,
-                         bool reverse = false);
+                         bool reverse = false, const int64_t* out_perm = nullptr);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -60,7 +60,7 @@ cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
                     T* x_new,
                     T* __restrict__ r,             // (nscales, r_rows, nsig)
                     int64_t r_rows, int nsig, int nscales,
-                    StepCoef<T> coef) {
+                    StepCoef<T> coef, const int64_t* __restrict__ out_perm) {
   const int lane = threadIdx.x & (G - 1);
   const int64_t group = (int64_t(blockIdx.x) * kStepThreads + threadIdx.x) / G;
   const int64_t row = row_begin + group;
@@ -72,6 +72,7 @@ cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
 
   const int start = __ldg(indptr + row);
   const int end = __ldg(indptr + row + 1);
+  const int64_t out_row = out_perm ? __ldg(out_perm + row) : row;   // x_new only
 
   // every lane of the group runs the same trip count (the shuffles below need
   // the whole group); lanes past the last column are merely predicated off
@@ -126,10 +127,10 @@ cheby_step_rowgroup(int64_t row_begin, int64_t row_end,
 #pragma unroll
         for (int v = 0; v < VEC; ++v) xn.v[v] = fma(coef.ck[i], sv.v[v], xn.v[v]);
       }
-      store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
+      store_vec_stream<T, VEC>(x_new + out_row * nsig + c0, xn);
       continue;
     }
-    store_vec_stream<T, VEC>(x_new + row * nsig + c0, xn);
+    store_vec_stream<T, VEC>(x_new + out_row * nsig + c0, xn);
 
     for (int i = 0; i < nscales; ++i) {
       T* rp = r + (int64_t(i) * r_rows + row) * nsig + c0;
@@ -169,7 +170,8 @@ template <typename T, int VEC, int G>
 static int launch_group(bool first, bool spmm, int64_t row_begin, int64_t row_end,
                         const int32_t* indptr, const int32_t* indices, const T* vals,
                         const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,
-                        int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st) {
+                        int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st,
+                        const int64_t* out_perm) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return GSP_OK;
   const int64_t blocks = ceil_div(rows * G, kStepThreads);
@@ -178,7 +180,7 @@ static int launch_group(bool first, bool spmm, int64_t row_begin, int64_t row_en
 #define GSP_GO(F, S)                                                                   \
   cheby_step_rowgroup<T, VEC, G, F, S><<<grid, block, 0, st>>>(                        \
       row_begin, row_end, indptr, indices, vals, x_cur, x_old, x_new, r, r_rows, nsig, \
-      nscales, coef)
+      nscales, coef, out_perm)
   if (first && spmm) GSP_GO(true, true);
   else if (first) GSP_GO(true, false);
   else if (spmm) GSP_GO(false, true);
@@ -192,10 +194,11 @@ template <typename T, int VEC>
 static int launch_vec(int groups_needed, bool first, bool spmm, int64_t rb, int64_t re,
                       const int32_t* indptr, const int32_t* indices, const T* vals,
                       const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,
-                      int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st) {
+                      int nsig, int nscales, const StepCoef<T>& coef, cudaStream_t st,
+                      const int64_t* out_perm) {
 #define GSP_CASE(GG)                                                                     \
   return launch_group<T, VEC, GG>(first, spmm, rb, re, indptr, indices, vals, x_cur,     \
-                                  x_old, x_new, r, r_rows, nsig, nscales, coef, st)
+                                  x_old, x_new, r, r_rows, nsig, nscales, coef, st, out_perm)
   if (groups_needed <= 1) GSP_CASE(1);
   if (groups_needed <= 2) GSP_CASE(2);
   if (groups_needed <= 4) GSP_CASE(4);
@@ -216,7 +219,7 @@ int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
                const int32_t* indices, const T* vals, const T* x_cur, const T* x_old,
                T* x_new, T* r, int64_t r_rows, int nsig, int nscales, const double* ck,
                const double* c0, double alpha, double beta, double gamma, cudaStream_t st,
-               bool add_source) {
+               bool add_source, const int64_t* out_perm) {
   constexpr int MV = MaxVec<T>::value;
   const bool vec_ok = (nsig % MV == 0) && aligned16(x_cur) && aligned16(x_new) &&
                       aligned16(r) && (first || aligned16(x_old));
@@ -236,10 +239,10 @@ int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr,
       int rc;
       if (vec_ok)
         rc = launch_vec<T, MV>((nsig + MV - 1) / MV, first, true, rb, re, indptr, indices,
-                               vals, x_cur, x_old, x_new, rs, r_rows, nsig, ns, coef, st);
+                               vals, x_cur, x_old, x_new, rs, r_rows, nsig, ns, coef, st, out_perm);
       else
         rc = launch_vec<T, 1>(nsig, first, true, rb, re, indptr, indices, vals, x_cur,
-                              x_old, x_new, rs, r_rows, nsig, ns, coef, st);
+                              x_old, x_new, rs, r_rows, nsig, ns, coef, st, out_perm);
       if (rc != GSP_OK) return rc;
     } else {
       // remaining scales of a wide bank: r_i (+)= c_ik * x_new, no second SpMM
@@ -441,11 +444,11 @@ int spmm_plain(int64_t n, const int32_t* indptr, const int32_t* indices, const T
 template int cheby_step<float>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
                                const float*, const float*, const float*, float*, float*,
                                int64_t, int, int, const double*, const double*, double,
-                               double, double, cudaStream_t, bool);
+                               double, double, cudaStream_t, bool, const int64_t*);
 template int cheby_step<double>(bool, int64_t, int64_t, const int32_t*, const int32_t*,
                                 const double*, const double*, const double*, double*, double*,
                                 int64_t, int, int, const double*, const double*, double,
-                                double, double, cudaStream_t, bool);
+                                double, double, cudaStream_t, bool, const int64_t*);
 
 }  // namespace gsp
 

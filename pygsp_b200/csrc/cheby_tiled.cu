@@ -63,6 +63,7 @@ struct TileArgs {
   int reverse;            // walk the tiles from the last to the first (see cheby_op)
   int64_t n_front;        // tiles [0, n_front) always run first, in order (halo: boundary tiles)
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
+  const int64_t* out_perm;  // x_new row of local row i is out_perm[i] (NULL: i); last step of a partitioned call
 };
 
 // ----------------------------------------------------------------- PTX helpers
@@ -379,7 +380,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           xn.w = fmaf(w, sv.w, xn.w);
         }
       }
-      store_f4(xn_tile + off, xn, keep_writes);
+      if (a.out_perm)      // the caller's row order: local row -> original row (uniform branch)
+        store_f4(a.x_new + __ldg(a.out_perm + r0 + lr) * NS + c0, xn, keep_writes);
+      else
+        store_f4(xn_tile + off, xn, keep_writes);
       if (push_tile) {
         // fused halo push: this row's new value goes straight into the halo rows of
         // the neighbours that reference it (peer stores over NVLink)
@@ -547,8 +551,10 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
-                         int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse) {
+                         int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse,
+                         const int64_t* out_perm) {
   TileArgs a;
+  a.out_perm = out_perm;
   a.keep_writes = env_int("GSPB200_TILE_REV", 1);
   a.reverse = (reverse && a.keep_writes) ? 1 : 0;
   a.add_source = add_source ? 1 : 0;
@@ -557,6 +563,12 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
   GSP_REQUIRE(!add_source || (nscales >= 1 && !first), "add_source needs source blocks");
   memset(&a.halo, 0, sizeof(a.halo));
   const int64_t full_tiles = (re - rb) / plan.rows_per_tile;
+  gsp_halo_fusion probe;                       // GSPB200_FORCE_HALO=1: run the halo-capable
+  if (!halo && rb == 0 && env_int("GSPB200_FORCE_HALO", 0)) {   // variant with no neighbours
+    memset(&probe, 0, sizeof(probe));          // (single-GPU A/B of the two instantiations)
+    probe.n_owned = 0x7fffffff;
+    halo = &probe;
+  }
   if (halo) {
     a.halo = *halo;
     const int R = plan.rows_per_tile;

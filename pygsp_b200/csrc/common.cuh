@@ -62,7 +62,13 @@ template <typename T>
 int cheby_step(bool first, int64_t rb, int64_t re, const int32_t* indptr, const int32_t* indices,
                const T* vals, const T* x_cur, const T* x_old, T* x_new, T* r, int64_t r_rows,
                int nsig, int nscales, const double* ck, const double* c0, double alpha,
-               double beta, double gamma, cudaStream_t st, bool add_source = false);
+               double beta, double gamma, cudaStream_t st, bool add_source = false,
+               const int64_t* out_perm = nullptr);   // x_new row of local row i is out_perm[i]
+
+// dst[i,:] = src[idx[i],:] (scatter: dst[idx[i],:] = src[i,:]) -- csrc/graph.cu
+template <typename T>
+int move_rows(bool scatter, int64_t rows, const int64_t* idx, const T* src, int64_t width, T* dst,
+              cudaStream_t st);
 
 // ----- vector types: 16-byte packets of T --------------------------------
 template <typename T, int VEC> struct Pack;

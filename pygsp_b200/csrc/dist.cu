@@ -22,7 +22,8 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
                          int nscales, const double* ck, const double* c0, double alpha, double beta,
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
-                         int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse);
+                         int64_t* rows_done, cudaStream_t st, bool add_source, bool reverse,
+                         const int64_t* out_perm);
 
 template <typename T> struct DistTraits;
 template <> struct DistTraits<float> {
@@ -51,7 +52,8 @@ static int dist_step(const gsp_dist_plan* p, const gsp_tile_plan* tile, bool fus
                      const T* x_cur, const T* x_old, T* x_new, int new_buf, T* r, int64_t r_rows,
                      int nsig, int nscales, const double* ck, const double* c0, double alpha,
                      double beta, double gamma, bool add_source, bool reverse, uint64_t wait_value,
-                     uint64_t publish_value, bool publish, void* stream) {
+                     uint64_t publish_value, bool publish, void* stream,
+                     const int64_t* out_perm = nullptr) {
   cudaStream_t st = as_stream(stream);
   const int64_t n = p->n_local;
   if (fused) {
@@ -80,17 +82,18 @@ static int dist_step(const gsp_dist_plan* p, const gsp_tile_plan* tile, bool fus
                                   reinterpret_cast<const float*>(x_old),
                                   reinterpret_cast<float*>(x_new), reinterpret_cast<float*>(r),
                                   r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *tile, &h, &done,
-                                  st, add_source, reverse);
+                                  st, add_source, reverse, out_perm);
     if (rc != GSP_OK) return rc;
     // remainder rows (< rows_per_tile; interior by the fused-form condition)
     return cheby_step<T>(first, done, n, p->indptr, p->indices, static_cast<const T*>(p->data), x_cur,
                          x_old, x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st,
-                         add_source);
+                         add_source, out_perm);
   }
   int rc = gsp_halo_wait(p->flags, p->neighbor_ids, p->n_neighbors, wait_value, stream);
   if (rc != GSP_OK) return rc;
   rc = cheby_step<T>(first, 0, n, p->indptr, p->indices, static_cast<const T*>(p->data), x_cur, x_old,
-                     x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st, add_source);
+                     x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st, add_source,
+                     out_perm);
   if (rc != GSP_OK) return rc;
   if (publish) return DistTraits<T>::push(p, p->n_send, new_buf, publish_value, nsig, stream);
   return GSP_OK;
@@ -123,15 +126,26 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
   if (rc != GSP_OK) return rc;
   rc = gsp_halo_wait(p->flags, p->neighbor_ids, p->n_neighbors, base + 1, stream);
   if (rc != GSP_OK) return rc;
-  if (x && x != buf[0])
+  const int64_t* perm = p->perm;      // local row i is row perm[i] of the caller's block
+  if (x && perm) {
+    rc = move_rows<T>(false, n, perm, x, nsig, buf[0], st);
+    if (rc != GSP_OK) return rc;
+  } else if (x && x != buf[0]) {
     GSP_CUDA(cudaMemcpyAsync(buf[0], x, sizeof(T) * size_t(n) * nsig, cudaMemcpyDeviceToDevice, st));
+  }
   rc = DistTraits<T>::push(p, p->n_send, 0, base + 2, nsig, stream);
   if (rc != GSP_OK) return rc;
 
   double ck[16], c0[16], zero[16];
   for (int i = 0; i < 16; ++i) zero[i] = 0;
   if (!clenshaw) {
-    // forward recurrence, reference order (approximations.py:99-112)
+    // forward recurrence, reference order (approximations.py:99-112).  With a row
+    // permutation the accumulators live in local order in stream-ordered scratch and are
+    // scattered to the caller's order at the end.
+    T* r_out = r;
+    if (perm && n > 0) {
+      GSP_CUDA(cudaMallocAsync((void**)&r, sizeof(T) * size_t(nscales) * n * nsig, st));
+    }
     int cur = 0, old = 1;
     for (int k = 1; k <= K; ++k) {
       for (int i = 0; i < nscales; ++i) {
@@ -143,10 +157,16 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
                         n, nsig, nscales, ck, c0, first ? 2.0 / lmax : 4.0 / lmax,
                         first ? -1.0 : -2.0, first ? 0.0 : -1.0, false, (k & 1) == 0,
                         base + 1 + k, base + 2 + k, k < K, stream);
-      if (rc != GSP_OK) return rc;
+      if (rc != GSP_OK) { if (r != r_out) cudaFreeAsync(r, st); return rc; }
       std::swap(cur, old);
     }
-    return GSP_OK;
+    if (r != r_out) {
+      for (int i = 0; i < nscales && rc == GSP_OK; ++i)
+        rc = move_rows<T>(true, n, perm, r + int64_t(i) * n * nsig, nsig, r_out + int64_t(i) * n * nsig,
+                          st);
+      cudaFreeAsync(r, st);
+    }
+    return rc;
   }
   // Clenshaw, single filter (see cheby_clenshaw in cheby.cu): buf[0] keeps x (the source),
   // b_{K-1} -> buf[1], b_{K-2} -> buf[2], b_{K-3} -> buf[1], ...; the last step writes r.
@@ -171,7 +191,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
     T* x_new = last ? r : buf[dst];
     rc = dist_step<T>(p, tile, fused, false, buf[cur], buf[old_buf], x_new, dst, buf[0], n, nsig, 1,
                       ck, zero, last ? 0.5 * a2 : a2, last ? -1.0 : -2.0, gamma, true, (k & 1) == 0,
-                      base + 1 + step, base + 2 + step, !last, stream);
+                      base + 1 + step, base + 2 + step, !last, stream, last ? perm : nullptr);
     if (rc != GSP_OK) return rc;
     old = cur;
     cur = dst;

@@ -391,27 +391,18 @@ __global__ void bounds_init_kernel(double* out) {
 }
 
 // ---- row gather: dst[i,:] = src[idx[i],:] (vertex reordering, halo pack) --------
-template <typename T>
-__global__ void gather_rows_kernel(int64_t rows, const int64_t* __restrict__ idx,
-                                   const T* __restrict__ src, int64_t width, T* __restrict__ dst) {
+// PACK = int4 when rows are 16-byte multiples and the bases are aligned (one 16-byte packet
+// per thread and trip, rows fully coalesced), else the element type.
+template <typename PACK, bool SCATTER>
+__global__ void move_rows_kernel(int64_t rows, const int64_t* __restrict__ idx,
+                                 const PACK* __restrict__ src, int64_t width, PACK* __restrict__ dst) {
   const int64_t total = rows * width;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (; i < total; i += stride) {
     const int64_t r = i / width, c = i - r * width;
-    dst[i] = src[idx[r] * width + c];
-  }
-}
-
-template <typename T>
-__global__ void scatter_rows_kernel(int64_t rows, const int64_t* __restrict__ idx,
-                                    const T* __restrict__ src, int64_t width, T* __restrict__ dst) {
-  const int64_t total = rows * width;
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (; i < total; i += stride) {
-    const int64_t r = i / width, c = i - r * width;
-    dst[idx[r] * width + c] = src[i];
+    if (SCATTER) dst[idx[r] * width + c] = src[i];
+    else dst[i] = src[idx[r] * width + c];
   }
 }
 
@@ -509,12 +500,25 @@ template <typename T>
 int move_rows(bool scatter, int64_t rows, const int64_t* idx, const T* src, int64_t width, T* dst,
               cudaStream_t st) {
   if (rows * width == 0) return GSP_OK;
-  const int blocks = (int)std::min<int64_t>(ceil_div(rows * width, 256), int64_t(sm_count()) * 32);
-  if (scatter) scatter_rows_kernel<T><<<blocks, 256, 0, st>>>(rows, idx, src, width, dst);
-  else gather_rows_kernel<T><<<blocks, 256, 0, st>>>(rows, idx, src, width, dst);
+  const bool vec = (width * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+  if (vec) {
+    const int64_t w = width * sizeof(T) / 16;
+    const int blocks = (int)std::min<int64_t>(ceil_div(rows * w, 256), int64_t(sm_count()) * 32);
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    if (scatter) move_rows_kernel<int4, true><<<blocks, 256, 0, st>>>(rows, idx, s4, w, d4);
+    else move_rows_kernel<int4, false><<<blocks, 256, 0, st>>>(rows, idx, s4, w, d4);
+  } else {
+    const int blocks = (int)std::min<int64_t>(ceil_div(rows * width, 256), int64_t(sm_count()) * 32);
+    if (scatter) move_rows_kernel<T, true><<<blocks, 256, 0, st>>>(rows, idx, src, width, dst);
+    else move_rows_kernel<T, false><<<blocks, 256, 0, st>>>(rows, idx, src, width, dst);
+  }
   GSP_LAUNCH_CHECK("move_rows");
   return GSP_OK;
 }
+template int move_rows<float>(bool, int64_t, const int64_t*, const float*, int64_t, float*, cudaStream_t);
+template int move_rows<double>(bool, int64_t, const int64_t*, const double*, int64_t, double*, cudaStream_t);
 
 }  // namespace gsp
 

@@ -251,10 +251,15 @@ class PartitionedCheby:
                                       True if clenshaw is None else clenshaw)
         bufs = [torch.empty((ext, nsig), dtype=self.dtype, device=self.device) for _ in range(2)]
         xin = x.to(self.dtype)
-        bufs[0][:n] = xin if local_order else xin.index_select(0, self.perm)
+        be = self.backend
+        if local_order:
+            bufs[0][:n] = xin
+        elif be.has_streams:
+            be.move_rows(xin.contiguous(), self.perm, bufs[0], scatter=False)
+        else:
+            bufs[0][:n] = xin.index_select(0, self.perm)
         r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
         plan = self._tile_plan(nsig, nscales)
-        be = self.backend
         halo_bytes = p.n_halo * nsig * bufs[0].element_size()
         overlap = self.overlap if self.overlap is not None else halo_bytes >= self.overlap_min_bytes
         overlap = bool(overlap) and be.has_streams and p.parts > 1
@@ -284,7 +289,11 @@ class PartitionedCheby:
         if local_order:
             return r
         out = torch.empty_like(r)
-        out[:, self.perm] = r
+        if be.has_streams:
+            for i in range(nscales):
+                be.move_rows(r[i], self.perm, out[i], scatter=True)
+        else:
+            out[:, self.perm] = r
         return out
 
     def filter_pinned(self, lmax, c, xh, clenshaw=None):
@@ -294,9 +303,9 @@ class PartitionedCheby:
         from .filters import pipeline
         c = np.atleast_2d(np.asarray(c, dtype=np.float64))
         p = self.plan          # the chunk width is derived from rank-independent sizes
-        width = pipeline.chunk_width(p.n_global // p.parts, int(xh.shape[1]), xh.element_size())
+        chunks = pipeline.chunk_plan(p.n_global // p.parts, int(xh.shape[1]), xh.element_size())
         return pipeline.run_pinned(lambda xc: self.cheby_op(lmax, c, xc, clenshaw=clenshaw),
-                                   self.device, self.dtype, xh, c.shape[0], width=width)
+                                   self.device, self.dtype, xh, c.shape[0], chunks=chunks)
 
     # ------------------------------------------------------------------- lmax
     def spmv(self, v):
@@ -385,14 +394,14 @@ class PartitionedCheby:
         if nsig not in self._windows:
             self._windows[nsig] = PeerWindow(self, nsig)
         win = self._windows[nsig]
-        xin = x.to(self.dtype)
-        if not local_order:
-            xin = xin.index_select(0, self.perm)
-        xin = xin.contiguous()
+        xin = x.to(self.dtype).contiguous()
         use_clenshaw = bool(clenshaw) and nscales == 1 and M >= 3
         r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
         plan = self._tile_plan(nsig, nscales) if self.fuse_halo else None
         seq = ctypes.c_uint64(self._seq)
+        # the row permutation (boundary rows first) is applied inside the call: the input is
+        # gathered straight into the window, the result is stored to the caller's rows
+        win.dist_plan.perm = None if local_order else self.perm.data_ptr()
         with torch.cuda.device(self.device):
             nat.call("gsp_cheby_op_dist_" + nat.suffix(self.dtype), win.dist_plan, plan,
                      nat.f64(lmax), c, nat.i32(nscales), nat.i32(M), xin, nat.i64(nsig), r,
@@ -400,11 +409,7 @@ class PartitionedCheby:
                      nat.stream_ptr(self.device))
         self._seq = int(seq.value)
         self.bytes_sent_per_step = int(win.src_row.numel()) * nsig * xin.element_size()
-        if local_order:
-            return r
-        out = torch.empty_like(r)
-        out[:, self.perm] = r
-        return out
+        return r
 
 
 class PeerWindow:
@@ -579,6 +584,14 @@ class _CudaBackend:
             nat.call("gsp_gather_rows_" + nat.suffix(buf.dtype), nat.i64(idx.numel()), idx, buf,
                      nat.i64(nsig), out, nat.stream_ptr(self.device))
         return out
+
+    def move_rows(self, src, idx, dst, scatter):
+        """dst[i,:] = src[idx[i],:] (scatter: dst[idx[i],:] = src[i,:]) for the rows of idx."""
+        torch = nat.require_cuda()
+        with torch.cuda.device(self.device):
+            nat.call(("gsp_scatter_rows_" if scatter else "gsp_gather_rows_") + nat.suffix(src.dtype),
+                     nat.i64(idx.numel()), idx, src, nat.i64(src.shape[1]), dst,
+                     nat.stream_ptr(self.device))
 
     def step(self, op, first, x_cur, x_old, x_new, r, nsig, nscales, ck, c0, coef, plan, rows):
         torch = nat.require_cuda()

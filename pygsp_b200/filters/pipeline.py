@@ -34,18 +34,29 @@ def _side_streams(device):
     return _streams[key]
 
 
-def chunk_width(n, nsig, itemsize, nscales=1):
-    """Column-chunk width for an (n, nsig) block: the widest split into >= 2 chunks whose width
-    the tiled kernel supports, provided a chunk still is a sizeable transfer (>= 8 MB) --
-    otherwise the whole block (no pipelining).  GSPB200_E2E_CHUNK overrides (0 = off)."""
+def chunk_plan(n, nsig, itemsize):
+    """Column chunks [(offset, width), ...] for an (n, nsig) block.
+
+    The first upload and the last download cannot overlap any computation, so the first
+    and the last chunk are NARROW (a quarter of the block each) and the middle one wide
+    (half: wide blocks run the recurrence more efficiently): 64 signals -> 16 | 32 | 16.
+    Every width is one the tiled kernel supports; blocks that are small (< 32 MB) or whose
+    width does not split that way are taken whole.  GSPB200_E2E_CHUNK=w forces equal chunks of
+    w signals (0 = no pipelining)."""
     env = os.environ.get("GSPB200_E2E_CHUNK")
     if env is not None:
         w = int(env)
-        return w if (w > 0 and nsig % w == 0) else nsig
-    for w in _TILED_WIDTHS:
-        if w <= nsig // 2 and nsig % w == 0 and n * w * itemsize >= (8 << 20):
-            return w
-    return nsig
+        if w > 0 and nsig % w == 0:
+            return [(o, w) for o in range(0, nsig, w)]
+        return [(0, nsig)]
+    q = nsig // 4
+    if nsig % 4 == 0 and q in _TILED_WIDTHS and 2 * q in _TILED_WIDTHS \
+            and n * nsig * itemsize >= (32 << 20):
+        return [(0, q), (q, 2 * q), (3 * q, q)]
+    h = nsig // 2
+    if nsig % 2 == 0 and h in _TILED_WIDTHS and n * nsig * itemsize >= (32 << 20):
+        return [(0, h), (h, h)]
+    return [(0, nsig)]
 
 
 def _copy2d(dst_ptr, dpitch, src_ptr, spitch, width, height, kind, stream, use_kernel):
@@ -60,14 +71,14 @@ def _copy2d(dst_ptr, dpitch, src_ptr, spitch, width, height, kind, stream, use_k
                  ctypes.c_size_t(height), nat.i32(kind), ctypes.c_void_p(stream.cuda_stream))
 
 
-def run_pinned(compute, device, dtype, xh, nscales, out=None, width=None):
+def run_pinned(compute, device, dtype, xh, nscales, out=None, chunks=None):
     """The three-stream pipeline for any column-separable operator.
 
     ``compute(x_chunk)`` maps an (n, w) device block to an (nscales, n, w) device tensor on the
     current stream (it may return a fresh tensor per call; references are kept until the
     downloads have finished).  ``xh``: contiguous pinned host tensor (n, nsig).  Returns the
-    pinned host tensor (nscales, n, nsig), complete on return.  ``width``: chunk width
-    (default: :func:`chunk_width`; callers whose ranks must agree pass it explicitly).
+    pinned host tensor (nscales, n, nsig), complete on return.  ``chunks``: [(offset, width)]
+    (default: :func:`chunk_plan`; callers whose ranks must agree pass it explicitly).
     """
     torch = nat.require_cuda()
     n, nsig = xh.shape
@@ -76,40 +87,29 @@ def run_pinned(compute, device, dtype, xh, nscales, out=None, width=None):
         raise ValueError("the pipelined path needs a contiguous pinned host tensor of the engine's dtype")
     if out is None:
         out = torch.empty((nscales, n, nsig), dtype=dtype, pin_memory=True)
-    w = width if width else chunk_width(n, nsig, item, nscales)
-    nchunks = nsig // w
+    chunks = chunks if chunks else chunk_plan(n, nsig, item)
+    nchunks = len(chunks)
     use_kernel = os.environ.get("GSPB200_STAGE", "dma") == "kernel"
     with torch.cuda.device(device):
         main = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device)
-        nbuf = min(2, nchunks)
-        xin = [torch.empty((n, w), dtype=dtype, device=device) for _ in range(nbuf)]
+        xin = [torch.empty((n, w), dtype=dtype, device=device) for _, w in chunks]
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        ev_in = [None] * nchunks
-        ev_comp = [None] * nchunks
+        ev_in = []
+        for (o, w), buf in zip(chunks, xin):           # uploads run back to back on their stream
+            _copy2d(buf.data_ptr(), w * item, xh.data_ptr() + o * item, nsig * item, w * item, n, 1,
+                    s_in, use_kernel)
+            ev_in.append(s_in.record_event())
         results = []
-
-        def upload(j):
-            b = j % nbuf
-            if j >= nbuf:                      # the buffer's previous chunk has been consumed
-                s_in.wait_event(ev_comp[j - nbuf])
-            _copy2d(xin[b].data_ptr(), w * item, xh.data_ptr() + j * w * item, nsig * item,
-                    w * item, n, 1, s_in, use_kernel)
-            ev_in[j] = s_in.record_event()
-
-        upload(0)
-        for j in range(nchunks):
-            if j + 1 < nchunks:
-                upload(j + 1)
+        for j, (o, w) in enumerate(chunks):
             main.wait_event(ev_in[j])
-            res = compute(xin[j % nbuf])
+            res = compute(xin[j])
             results.append(res)
-            ev_comp[j] = main.record_event()
-            s_out.wait_event(ev_comp[j])
+            s_out.wait_event(main.record_event())
             for i in range(nscales):
-                _copy2d(out[i].data_ptr() + j * w * item, nsig * item, res[i].data_ptr(),
-                        w * item, w * item, n, 2, s_out, use_kernel)
+                _copy2d(out[i].data_ptr() + o * item, nsig * item, res[i].data_ptr(), w * item,
+                        w * item, n, 2, s_out, use_kernel)
         main.wait_stream(s_in)
         main.wait_stream(s_out)
         main.synchronize()                     # a host result must be complete on return

@@ -670,8 +670,8 @@ def test_pinned_host_pipeline_equals_device_path(gsp, monkeypatch, stage, nf):
     # and against the oracle
     Lo = G.L.to_scipy().astype(np.float64)
     ref = orc.filter_signal(Lo, G.lmax, orc.heat_kernels(G.lmax, [10, 20, 40][:nf] if nf > 1 else 50),
-                            x[:, :3].double().cpu().numpy(), order=20)
-    assert relerr_cols(got.numpy()[:, :3].reshape(ref.shape), ref) <= F32_TOL
+                            x[:, :4].double().cpu().numpy(), order=20)     # 4 != Nf: signals
+    assert relerr_cols(got.numpy()[:, :4].reshape(ref.shape), ref) <= F32_TOL
 
 
 def test_clenshaw_is_the_default_for_one_filter(gsp, sensor5k):
