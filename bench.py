@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--vertices", dest="n", type=int, default=None,
                     help="override the per-GPU vertex count")
+    ap.add_argument("--k", type=int, default=None, help="override the k of the k-NN workloads (probes)")
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: config2 on one GPU, knn10m (strong scaling) on N > 1")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -133,6 +134,8 @@ def pick_workload(args, world):
     wl = dict(WORKLOADS[name])
     if args.n:
         wl["N"] = args.n
+    if args.k:
+        wl["k"] = args.k
     scaling = "weak" if (world > 1 and name == "config2") else "strong"
     return name, wl, scaling
 
@@ -471,6 +474,31 @@ def build_partitioned_strips(gsp, wl, rank, world, torch, dist):
     return op, op.estimate_lmax(), int(L_rows.nnz)       # distributed Lanczos, as on one GPU
 
 
+def build_partitioned_knn_slabs(gsp, wl, rank, world, torch, dist):
+    """BASELINE configs[4] (and its smaller instances): rank q generates slab q of ONE k-NN
+    graph of N uniform points in the unit cube on its GPU (graphs.KnnSlabs: grid-hash k-NN,
+    NNGraph's Gaussian weights and 'average' symmetrisation, Morton numbering inside the slab),
+    assembles its rows of L in HBM and plans its halo on the device."""
+    from pygsp_b200 import distributed as gd
+    from pygsp_b200.graphs.generators import KnnSlabs
+    n_per = wl["N"] // world
+    gen = KnnSlabs(rank, world, n_per, dim=3 if wl["graph"] == "knn3d" else 2, k=wl["k"],
+                   seed=wl["seed"])
+    tot = torch.tensor(gen.distance_sum(), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    sigma = float(tot[0] / tot[1])
+    ptr, idx, val, _ = gen.laplacian_rows_device(sigma)
+    del gen
+    torch.cuda.empty_cache()
+    plan = gd.HaloPlan.from_device(ptr, idx, val, gd.even_bounds(n_per * world, world), rank)
+    del ptr, idx, val
+    torch.cuda.empty_cache()
+    op = gd.PartitionedCheby(plan, dtype=torch.float32, exchange=os.environ.get("GSPB200_EXCHANGE"))
+    op.fuse_halo = os.environ.get("GSPB200_FUSE_HALO", "1") != "0"
+    return op, op.estimate_lmax(), int(plan.nnz)
+
+
 def build_partitioned_from_graph(G, rank, world, torch):
     """Strong scaling: every rank holds the SAME graph (built through the Graph API with the
     same seed, exactly the one-GPU graph) and keeps the row block [N p/P, N (p+1)/P) of its
@@ -525,7 +553,8 @@ def run_ours(args):
     G = op = None
     lo = 0
     t_build0 = time.perf_counter()
-    if world == 1 or (scaling == "strong" and wl["graph"] in ("sensor", "grid2d")):
+    if wl["graph"] != "knn3d" and (world == 1 or (scaling == "strong"
+                                                  and wl["graph"] in ("sensor", "grid2d"))):
         G = build_graph(gsp, wl)                     # the one-GPU graph, on every rank
         n_global = wl["N"] = G.N
         lmax, nnz_global = G.lmax, G.L.nnz
@@ -538,6 +567,8 @@ def run_ours(args):
     else:
         if wl["graph"] == "sbm":
             op, lmax, nnz = build_partitioned_sbm(gsp, wl, rank, world, torch, dist)
+        elif wl["graph"] == "knn3d":
+            op, lmax, nnz = build_partitioned_knn_slabs(gsp, wl, rank, world, torch, dist)
         else:
             op, lmax, nnz = build_partitioned_strips(gsp, wl, rank, world, torch, dist)
         n = op.plan.n_local
@@ -550,7 +581,8 @@ def run_ours(args):
         bank = gsp.filters.Heat(g, scale=wl["scale"])
         c = np.atleast_2d(gsp.filters.compute_cheby_coeff(bank, m=order))
         t = torch.tensor([nnz], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
+        if world > 1:
+            dist.all_reduce(t)
         nnz_global = int(t.item())
     t_build = time.perf_counter() - t_build0
     clen = c.shape[0] == 1                           # the engine's default form for one filter
@@ -559,7 +591,7 @@ def run_ours(args):
     gen = torch.Generator(device="cuda").manual_seed(0 if G is not None else rank)
     x_full = torch.randn(n_global if G is not None else n, nsig, device="cuda", generator=gen)
     x = x_full[lo:lo + n].contiguous() if (G is not None and world > 1) else x_full
-    if world == 1:
+    if world == 1 and G is not None:
         run_dev = device_op(apx, G.L, lmax, c)
         run_host = lambda xh: bank.filter(xh, order=order)
     else:
@@ -638,9 +670,34 @@ def run_ours(args):
         if rank == 0:        # and the engine itself against the float64 oracle on one column
             col = x_full[:, :1].contiguous()
             parity["parity_rel_err_one_column_vs_oracle"] = oracle_parity(G.L, lmax, c, col, single(col))
-    elif world > 1:
-        parity["parity_rel_err"] = None
-        parity["parity_note"] = "no rank holds the whole graph for this workload; see tests/"
+    else:
+        # No rank holds the whole graph.  Two size-independent checks on every rank:
+        # (1) L 1 = 0, so filtering the constant signal must return p(0) = c_0/2 + sum_k (-1)^k c_k
+        #     on every vertex -- a stale or missing halo row breaks it at the boundary rows;
+        # (2) the packed NCCL exchange and the fused peer-store exchange are different transports
+        #     around the same kernels: their results on 8 signals must agree bit for bit.
+        k_idx = np.arange(c.shape[1])
+        p0 = float(0.5 * c[0, 0] + (c[0, 1:] * (-1.0) ** k_idx[1:]).sum())
+        ones = torch.ones(n, 8, device="cuda")
+        got = op.cheby_op(lmax, c, ones)
+        parity["parity_constant_signal_rel_err"] = allmax(float((got - p0).abs().max() / abs(p0)))
+        if world > 1:
+            from pygsp_b200 import distributed as gd
+            other = "nccl" if op._exchange_mode(8) == "p2p" else "p2p"
+            op_b = gd.PartitionedCheby(op.plan, dtype=torch.float32, exchange=other)
+            xs = x[:, :8].contiguous()
+            a8 = op.cheby_op(lmax, c, xs, clenshaw=False)
+            b8 = op_b.cheby_op(lmax, c, xs, clenshaw=False)
+            parity["parity_exchange_transports_bit_identical"] = allmax(
+                0.0 if torch.equal(a8, b8) else 1.0) == 0.0
+            parity["parity_rel_err"] = allmax(float((a8 - b8).abs().max() / a8.abs().max()))
+            del op_b, a8, b8
+        else:
+            parity["parity_rel_err"] = parity["parity_constant_signal_rel_err"]
+        parity["parity_note"] = ("no rank holds the whole graph for this workload: constant-signal "
+                                 "property + transport cross-check here; oracle parity of the same "
+                                 "generator and operator at test size in tests/test_distributed_gpu.py")
+        del got, ones
 
     if rank != 0:
         dist.barrier()

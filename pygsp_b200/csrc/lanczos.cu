@@ -86,26 +86,55 @@ spmv_subwarp_kernel(int64_t n, const int32_t* __restrict__ indptr,
     if (beta_out && blockIdx.x == 0 && threadIdx.x == 0) *beta_out = nb;
   }
   constexpr int RPB = kVecThreads / LPR;          // rows per block and pass
-  const int lane = threadIdx.x % LPR;
-  const int sub = threadIdx.x / LPR;
+  constexpr int U = 4;                            // independent rows per lane group and trip:
+  const int lane = threadIdx.x % LPR;             // a row is three dependent loads (indptr ->
+  const int sub = threadIdx.x / LPR;              // entry -> x[col]); U of them are in flight
   double dot = 0;
-  for (int64_t base = int64_t(blockIdx.x) * RPB; base < n; base += int64_t(gridDim.x) * RPB) {
-    const int64_t row = base + sub;                // the trip count is uniform over the block
-    const bool valid = row < n;
-    int start = 0, end = 0;
-    if (valid) {
-      start = __ldg(indptr + row);
-      end = __ldg(indptr + row + 1);
-    }
-    double acc = 0;
-    for (int j = start + lane; j < end; j += LPR)
-      acc += double(__ldg(vals + j)) * double(__ldg(x + __ldg(indices + j)));
+  for (int64_t base = int64_t(blockIdx.x) * (RPB * U); base < n;
+       base += int64_t(gridDim.x) * (RPB * U)) {   // the trip count is uniform over the block
+    int start[U], end[U];
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LPR);
-    if (valid && lane == 0) {
-      const double yi = acc * scale;
-      y[row] = T(yi);
-      if (dot_parts) dot += double(T(yi)) * (double(x[row]) * scale);
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * RPB + sub;
+      start[u] = end[u] = 0;
+      if (row < n) {
+        start[u] = __ldg(indptr + row);
+        end[u] = __ldg(indptr + row + 1);
+      }
+    }
+    double acc[U];
+    int col[U];
+    T val[U];
+    int more = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                   // first entry of every row: loads issued together
+      acc[u] = 0;
+      const int j = start[u] + lane;
+      const bool ok = j < end[u];
+      col[u] = ok ? __ldg(indices + j) : -1;
+      val[u] = ok ? __ldg(vals + j) : T(0);
+      more |= (j + LPR < end[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (col[u] >= 0) acc[u] = double(val[u]) * double(__ldg(x + col[u]));
+    if (__any_sync(0xffffffffu, more)) {            // rows longer than LPR entries
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        for (int j = start[u] + lane + LPR; j < end[u]; j += LPR)
+          acc[u] += double(__ldg(vals + j)) * double(__ldg(x + __ldg(indices + j)));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double a = acc[u];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o, LPR);
+      const int64_t row = base + u * RPB + sub;
+      if (row < n && lane == 0) {
+        const double yi = a * scale;
+        y[row] = T(yi);
+        if (dot_parts) dot += double(T(yi)) * (double(x[row]) * scale);
+      }
     }
   }
   if (dot_parts) {                                 // uniform branch
@@ -122,7 +151,7 @@ static inline int spmv_lanes(int64_t n, int64_t nnz) {
 }
 
 static inline int spmv_blocks(int64_t n, int lpr) {
-  const int64_t rpb = kVecThreads / lpr;
+  const int64_t rpb = (kVecThreads / lpr) * 4;        // U = 4 rows per lane group and trip
   return (int)std::max<int64_t>(
       1, std::min<int64_t>(ceil_div(n, rpb), std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks)));
 }

@@ -106,9 +106,72 @@ class HaloPlan:
         requested, self.send_counts = exchange_ids(self.halo_ids, self.recv_counts, rank, P, group)
         self.send_idx = inv[requested - lo]              # local-order rows to pack, grouped by peer
 
+    @classmethod
+    def from_device(cls, indptr, indices, data, bounds, rank, group=None, exchange_ids=None):
+        """The same plan from a row block that already lives in HBM (CUDA tensors ``indptr``
+        (n_local + 1), ``indices`` (GLOBAL column ids), ``data``): every nnz-sized step runs as
+        torch device ops and the local CSR stays on the device (``indices`` / ``data`` /
+        ``indptr`` are CUDA tensors, everything row- or halo-sized is NumPy as usual).  Used by
+        the graphs that are generated per rank on the GPU (bench config 5, strong scaling)."""
+        import torch
+        self = cls.__new__(cls)
+        bounds = np.asarray(bounds, dtype=np.int64)
+        P = len(bounds) - 1
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        n_local = hi - lo
+        if indptr.numel() != n_local + 1:
+            raise ValueError("rows must hold exactly the rank's row block")
+        dev = indices.device
+        self.rank, self.parts, self.bounds = rank, P, bounds
+        self.n_local, self.n_global = n_local, int(bounds[-1])
+        ptr = indptr.long()
+        counts = ptr[1:] - ptr[:-1]
+        cols = indices.long()
+        owned = (cols >= lo) & (cols < hi)
+        halo_ids = torch.unique(cols[~owned])                    # sorted
+        self.halo_ids = halo_ids.cpu().numpy()
+        owner = np.searchsorted(bounds, self.halo_ids, side="right") - 1
+        self.recv_counts = np.bincount(owner, minlength=P).astype(np.int64)
+        self.n_halo = int(self.halo_ids.size)
+        row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), counts)
+        is_boundary = torch.zeros(n_local, dtype=torch.bool, device=dev)
+        is_boundary[row_of[~owned]] = True
+        boundary = torch.nonzero(is_boundary).flatten()
+        interior = torch.nonzero(~is_boundary).flatten()
+        pad = min((-int(boundary.numel())) % 4, int(interior.numel()))
+        perm = torch.cat([boundary, interior])
+        self.n_boundary = int(boundary.numel()) + pad
+        self.n_true_boundary = int(boundary.numel())
+        inv = torch.empty(n_local, dtype=torch.int64, device=dev)
+        inv[perm] = torch.arange(n_local, device=dev)
+        self.perm, self.inv_perm = perm.cpu().numpy(), inv.cpu().numpy()
+        del row_of, is_boundary
+        new_counts = counts[perm]
+        new_ptr = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(new_counts, 0, out=new_ptr[1:])
+        nnz = int(new_ptr[-1].item())
+        if nnz >= 2 ** 31 or n_local + self.n_halo >= 2 ** 31:
+            raise ValueError("local block must fit int32 indices")
+        gather = torch.repeat_interleave(ptr[:-1][perm] - new_ptr[:-1], new_counts) + \
+            torch.arange(nnz, device=dev)
+        c = cols[gather]
+        del cols, owned
+        mine = (c >= lo) & (c < hi)
+        local = torch.where(mine, inv[(c - lo).clamp_(0, max(n_local - 1, 0))],
+                            n_local + torch.searchsorted(halo_ids, c))
+        self.indptr = new_ptr.int()
+        self.indices = local.int()
+        self.data = data[gather]
+        del gather, c, mine, local
+        if exchange_ids is None:
+            exchange_ids = _exchange_ids_torch
+        requested, self.send_counts = exchange_ids(self.halo_ids, self.recv_counts, rank, P, group)
+        self.send_idx = self.inv_perm[requested - lo]
+        return self
+
     @property
     def nnz(self):
-        return int(self.indices.size)
+        return int(self.indices.numel() if hasattr(self.indices, "numel") else self.indices.size)
 
 
 def _exchange_ids_torch(halo_ids, recv_counts, rank, P, group):
@@ -157,7 +220,8 @@ class PartitionedCheby:
         # halo is 3 % faster unsplit).  None = decide per call from the halo size.
         self.overlap = overlap
         self.overlap_min_bytes = 16 << 20
-        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dt)
+        t = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(
+            np.ascontiguousarray(a))).to(device=self.device, dtype=dt)
         self.indptr = t(plan.indptr, torch.int32)
         self.indices = t(plan.indices, torch.int32)
         self.data = t(plan.data, self.dtype)

@@ -285,6 +285,187 @@ class SensorStrips:
         return sparse.csr_matrix((S.data, gcol, S.indptr), shape=(self.n_per, n_global))
 
 
+def morton_order_device(coords, bits=None):
+    """:func:`morton_order` on the GPU: the same integer codes (float64 quantisation, bit
+    interleave) and a stable sort, so the permutation is identical to the host one."""
+    torch = nat.require_cuda()
+    n, d = coords.shape
+    if bits is None:
+        bits = 21 if d <= 3 else 64 // d
+    c = coords.to(torch.float64)
+    lo = c.min(dim=0).values
+    span = torch.clamp(c.max(dim=0).values - lo, min=1e-300)
+    q = torch.clamp(((c - lo) / span * float(1 << bits)).to(torch.int64), max=(1 << bits) - 1)
+    code = torch.zeros(n, dtype=torch.int64, device=coords.device)
+    for b in range(bits):
+        for k in range(d):
+            code |= ((q[:, k] >> b) & 1) << (b * d + k)
+    return torch.sort(code, stable=True).indices
+
+
+def _unit_ball(dim):
+    return {2: np.pi, 3: 4.0 * np.pi / 3.0}[dim]
+
+
+class KnnSlabs:
+    r"""Row block of ONE k-NN graph of ``parts * n_per`` points in the unit square / cube.
+
+    Input of the partitioned path for BASELINE configs[4] (synthetic k-NN point cloud, k = 16,
+    3-D, 5e7 points on 8 GPUs) and, in 2-D, the strong-scaling twin of ``Sensor``.  Slab q =
+    ``{x_0 in [q/P, (q+1)/P)}`` holds ``n_per`` uniform points (``default_rng(seed + q)``,
+    Morton-numbered inside the slab, global ids ``q * n_per ...``) and is rank q's row block.
+    A rank regenerates its two neighbour slabs and keeps their points within ``2 m`` of its
+    faces, searches the k nearest neighbours of every kept point on the GPU (``gsp_knn_grid``)
+    and uses the lists of its own points and of the neighbour points within ``m`` (their
+    search balls lie inside the kept set when every k-th distance is <= m, which is checked).
+    Weights, sigma = global mean neighbour distance and the 'average' symmetrisation are
+    NNGraph's (pygsp/graphs/nngraphs/nngraph.py:213-226,289-297); the result is exactly the row
+    block of the graph of the union of all slabs (tests compare with ``NNGraph``).
+    ``backend='host'`` runs the same plan with scipy's cKDTree (CPU tests of the host logic).
+    """
+
+    def __init__(self, rank, parts, n_per, dim=3, k=16, seed=0, backend="device",
+                 margin_factor=2.5, device=None):
+        self.rank, self.parts, self.n_per, self.dim, self.k = rank, parts, n_per, dim, k
+        self.backend = backend
+        n_global = parts * n_per
+        self.n_global = n_global
+        r_mean = (k / (_unit_ball(dim) * n_global)) ** (1.0 / dim)
+        self.margin = m = margin_factor * r_mean
+        if parts > 1 and 2 * m > 1.0 / parts:
+            raise ValueError("slabs thinner than the search margin: fewer parts or more points")
+        strips = [q for q in (rank - 1, rank, rank + 1) if 0 <= q < parts]
+        x_lo, x_hi = rank / parts, (rank + 1) / parts
+        pts, gid, near = [], [], []
+        for q in strips:
+            p = np.random.default_rng(seed + q).uniform(0, 1, (n_per, dim))
+            p[:, 0] = (p[:, 0] + q) / parts
+            if backend == "device":
+                torch = nat.require_cuda()
+                dev = _device_of(device)
+                pt = torch.from_numpy(p).to(dev)
+                pt = pt[morton_order_device(pt)]
+                ids = torch.arange(q * n_per, (q + 1) * n_per, device=dev)
+                if q != rank:
+                    dist = (x_lo - pt[:, 0]) if q < rank else (pt[:, 0] - x_hi)
+                    keep = dist < 2 * m
+                    pt, ids, dist = pt[keep], ids[keep], dist[keep]
+                    near.append(dist < m)
+                else:
+                    near.append(torch.ones(n_per, dtype=torch.bool, device=dev))
+                    self.own_lo = int(sum(x.shape[0] for x in pts))
+            else:
+                p = p[morton_order(p)]
+                ids = np.arange(q * n_per, (q + 1) * n_per)
+                if q != rank:
+                    dist = (x_lo - p[:, 0]) if q < rank else (p[:, 0] - x_hi)
+                    keep = dist < 2 * m
+                    p, ids, dist = p[keep], ids[keep], dist[keep]
+                    near.append(dist < m)
+                else:
+                    near.append(np.ones(n_per, dtype=bool))
+                    self.own_lo = int(sum(x.shape[0] for x in pts))
+                pt = p
+            pts.append(pt)
+            gid.append(ids)
+        if backend == "device":
+            torch = nat.require_cuda()
+            self.points = torch.cat(pts)
+            self.gid = torch.cat(gid)
+            self.used = torch.cat(near)
+            self.coords = self.points[self.own_lo:self.own_lo + n_per]
+            self.NN, self.D = knn_device(self.points, k, self.points.device)
+            kth = float(self.D[self.used, -1].max().item())
+        else:
+            self.points = np.concatenate(pts)
+            self.gid = np.concatenate(gid)
+            self.used = np.concatenate(near)
+            self.coords = self.points[self.own_lo:self.own_lo + n_per]
+            D, NN = spatial.cKDTree(self.points).query(self.points, k=k + 1, workers=-1)
+            self.D, self.NN = D[:, 1:], NN[:, 1:]
+            kth = float(self.D[self.used, -1].max())
+        if parts > 1 and kth > m:
+            raise RuntimeError("search margin too small for this density (k-th distance %g > %g): "
+                               "raise margin_factor" % (kth, m))
+
+    def distance_sum(self):
+        """(sum, count) of the own points' neighbour distances: sigma = global mean."""
+        d = self.D[self.own_lo:self.own_lo + self.n_per]
+        if self.backend == "device":
+            return float(d.sum(dtype=d.dtype).item()), int(d.numel())
+        return float(d.sum()), int(d.size)
+
+    def adjacency_rows(self, sigma):
+        """W[rows of this rank, :] as a host CSR with GLOBAL column ids (host backend)."""
+        m, k = self.points.shape[0], self.k
+        D, NN, used = self.D, self.NN, self.used
+        if self.backend == "device":
+            D, NN, used = D.cpu().numpy(), NN.cpu().numpy().astype(np.int64), used.cpu().numpy()
+        gid = self.gid if self.backend != "device" else self.gid.cpu().numpy()
+        src = np.repeat(np.flatnonzero(used), k)
+        A = sparse.csr_matrix((np.exp(-D[used].ravel() ** 2 / float(sigma)),
+                               (src, NN[used].ravel())), shape=(m, m))
+        S = ((A + A.T) / 2).tocsr()[self.own_lo:self.own_lo + self.n_per]
+        S.sort_indices()
+        # kept points are in ascending global order, so renaming keeps the rows sorted
+        return sparse.csr_matrix((S.data, gid[S.indices], S.indptr),
+                                 shape=(self.n_per, self.n_global))
+
+    def laplacian_rows_device(self, sigma, dtype=None):
+        """Rows of L = D - W of this rank, built in HBM: (indptr int32, indices int32 GLOBAL
+        ids, data) tensors in canonical CSR order (sorted rows, diagonal in place), and dw."""
+        torch = nat.require_cuda()
+        if self.backend != "device":
+            raise ValueError("laplacian_rows_device needs backend='device'")
+        dev, dt = self.points.device, _torch_dtype(torch, dtype)
+        m, k, n = int(self.points.shape[0]), self.k, self.n_per
+        # unused rows (kept points farther than `margin` from the slab) get zero-weight lists:
+        # an infinite distance gives exp(-inf) = 0 and the zeros are dropped below
+        dist = torch.where(self.used[:, None], self.D, torch.full_like(self.D, float("inf")))
+        indptr = torch.empty(m + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(m * k, dtype=torch.int32, device=dev)
+        data = torch.empty(m * k, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            nat.call("gsp_knn_to_csr_" + nat.suffix(dt), nat.i64(m), nat.i32(k), self.NN, dist,
+                     nat.f64(sigma), indptr, indices, data, nat.stream_ptr(dev))
+        W = symmetrize_average_device(DeviceCSR(indptr, indices, data, (m, m)))
+        del indptr, indices, data, dist
+        ptr = W.indptr[self.own_lo:self.own_lo + n + 1].long()
+        a, b = int(ptr[0].item()), int(ptr[-1].item())
+        cols, vals = W.indices[a:b].long(), W.data[a:b]
+        counts = ptr[1:] - ptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), counts)
+        keep = vals != 0
+        rows, vals = rows[keep], vals[keep]
+        gcol = self.gid[cols[keep]]
+        del cols, keep, W
+        counts = torch.bincount(rows, minlength=n)
+        dw = torch.segment_reduce(vals.double(), "sum", lengths=counts)
+        # L row i = -W row i with dw_i inserted at the diagonal's sorted position
+        gdiag = self.gid[self.own_lo:self.own_lo + n]
+        before = gcol < gdiag[rows]
+        n_before = torch.segment_reduce(before.double(), "sum", lengths=counts).long()
+        has_diag = dw != 0                                  # isolated vertex: empty row (graph.py:620)
+        l_counts = counts + has_diag.long()
+        l_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(l_counts, 0, out=l_ptr[1:])
+        nnz = int(l_ptr[-1].item())
+        if nnz >= 2 ** 31:
+            raise ValueError("the rank's rows of L must fit int32 offsets (nnz = %d)" % nnz)
+        w_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=w_ptr[1:])
+        pos = torch.arange(rows.numel(), device=dev) - w_ptr[rows] + l_ptr[rows] + \
+            (~before & has_diag[rows]).long()
+        l_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        l_val = torch.empty(nnz, dtype=dt, device=dev)
+        l_idx[pos] = gcol.int()
+        l_val[pos] = -vals
+        dpos = (l_ptr[:-1] + n_before)[has_diag]
+        l_idx[dpos] = gdiag[has_diag].int()
+        l_val[dpos] = dw[has_diag].to(dt)
+        return l_ptr.int(), l_idx, l_val, dw
+
+
 def laplacian_rows(W_rows, row_offset):
     """Rows of the combinatorial Laplacian D - W from rows of a SYMMETRIC adjacency.
 
