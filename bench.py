@@ -506,7 +506,9 @@ def build_partitioned_from_graph(G, rank, world, torch):
     from pygsp_b200 import distributed as gd
     bounds = gd.even_bounds(G.N, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    plan = gd.HaloPlan(csr_row_block(G.L, lo, hi), bounds, rank)
+    ptr = G.L.indptr[lo:hi + 1]
+    a, b = int(ptr[0].item()), int(ptr[-1].item())
+    plan = gd.HaloPlan.from_device(ptr - a, G.L.indices[a:b], G.L.data[a:b], bounds, rank)
     op = gd.PartitionedCheby(plan, dtype=torch.float32, exchange=os.environ.get("GSPB200_EXCHANGE"))
     op.fuse_halo = os.environ.get("GSPB200_FUSE_HALO", "1") != "0"
     return op, (lo, hi)
@@ -596,7 +598,8 @@ def run_ours(args):
         run_host = lambda xh: bank.filter(xh, order=order)
     else:
         local_order = os.environ.get("GSPB200_BENCH_LOCAL_ORDER") == "1"    # diagnosis only
-        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=local_order)
+        form = {"0": False, "1": True}.get(os.environ.get("GSPB200_BENCH_CLENSHAW"))   # diagnosis
+        run_dev = lambda xx: op.cheby_op(lmax, c, xx, local_order=local_order, clenshaw=form)
         run_host = lambda xh: op.filter_pinned(lmax, c, xh)[0]
 
     # ---- device-resident throughput ("value")

@@ -64,6 +64,7 @@ struct TileArgs {
   int64_t n_front;        // tiles [0, n_front) always run first, in order (halo: boundary tiles)
   int add_source;         // Clenshaw form: x_new += sum_i ck[i] * (tile i of r), r is not written
   const int64_t* out_perm;  // x_new row of local row i is out_perm[i] (NULL: i); last step of a partitioned call
+  int vec_direct;           // x_old / r rows are read straight from global memory (not staged by TMA)
 };
 
 // ----------------------------------------------------------------- PTX helpers
@@ -168,6 +169,46 @@ __device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int co
   return ldg_f4(p);
 }
 
+// sum_j w_j x_cur[col_j, c0 : c0 + 4] over the stored entries [jb, je) of one row (slab-relative
+// offsets).  The slab offset is a multiple of 4, so groups of four CSR entries are 16-byte
+// aligned in shared memory: one LDS.128 brings four column indices, one four weights.  Slots
+// outside [jb, je) (row head / tail) are predicated off, so the sum runs over the row's entries
+// in stored order.  COH: the row may reference halo columns (boundary tiles of a partitioned
+// step) -- those are read coherently; interior tiles use the plain non-coherent gather only.
+template <int NS, bool COH>
+__device__ __forceinline__ float4 row_gather_sum(const int32_t* __restrict__ sm_col,
+                                                 const float* __restrict__ sm_val, int jb, int je,
+                                                 const float* __restrict__ xg, int n_owned) {
+  const unsigned span = unsigned(je - jb);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int jj = jb & ~3; jj < je; jj += 4) {
+    const int4 c4 = *reinterpret_cast<const int4*>(sm_col + jj);
+    const float4 w4 = *reinterpret_cast<const float4*>(sm_val + jj);
+    float4 xv[4];
+    bool ok[4];
+    const int base = jj - jb;
+    ok[0] = unsigned(base + 0) < span;
+    ok[1] = unsigned(base + 1) < span;
+    ok[2] = unsigned(base + 2) < span;
+    ok[3] = unsigned(base + 3) < span;
+    const int cq[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (ok[q]) xv[q] = gather_f4<COH>(xg, cq[q], NS, n_owned);
+    const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ok[q]) {
+        acc.x = fmaf(wq[q], xv[q].x, acc.x);
+        acc.y = fmaf(wq[q], xv[q].y, acc.y);
+        acc.z = fmaf(wq[q], xv[q].z, acc.z);
+        acc.w = fmaf(wq[q], xv[q].w, acc.w);
+      }
+    }
+  }
+  return acc;
+}
+
 template <int G, bool FIRST, int NSC, bool HALO>
 __global__ void __launch_bounds__(32 * 17, 2)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
@@ -176,7 +217,8 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   const int S = a.stages;
   const int NW = a.consumer_warps;
   const int nsig = a.nsig;
-  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST, S);
+  const bool VD = !FIRST && a.vec_direct != 0;     // CTA-uniform
+  const TileLayout lay(R, a.slab_cap, nsig, a.nscales, FIRST || VD, S);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + S;
   unsigned char* stage0 = smem + lay.bar_bytes;
@@ -240,8 +282,9 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       }
       const uint32_t slab = a1 > a0 ? uint32_t(a1 - a0) * 4u : 0u;
       const uint32_t tile_vec = uint32_t(R) * nsig * 4u;
+      const bool stage_vec = !FIRST && !VD;
       const uint32_t bytes = uint32_t(R) * 4u + 2u * slab +
-                             (FIRST ? 0u : tile_vec * (1 + a.nscales));
+                             (stage_vec ? tile_vec * (1 + a.nscales) : 0u);
       mbar_expect_tx(full + s, bytes);
       bulk_g2s(sm_ptr, a.indptr + r0, uint32_t(R) * 4u, full + s);
       if (hint) {
@@ -249,7 +292,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           bulk_g2s_hint(sm_col, a.indices + a0, slab, full + s, pol);
           bulk_g2s_hint(sm_val, a.vals + a0, slab, full + s, pol);
         }
-        if (!FIRST) {
+        if (stage_vec) {
           bulk_g2s_hint(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s, pol);
           for (int i = 0; i < a.nscales; ++i)
             bulk_g2s_hint(sm_vec + size_t(i + 1) * R * nsig,
@@ -260,7 +303,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           bulk_g2s(sm_col, a.indices + a0, slab, full + s);
           bulk_g2s(sm_val, a.vals + a0, slab, full + s);
         }
-        if (!FIRST) {
+        if (stage_vec) {
           bulk_g2s(sm_vec, a.x_old + r0 * nsig, tile_vec, full + s);
           for (int i = 0; i < a.nscales; ++i)
             bulk_g2s(sm_vec + size_t(i + 1) * R * nsig,
@@ -313,6 +356,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     const int a0 = sm_ptr[R + 4];
     const int64_t r0 = a.row_begin + tile * R;
     const bool push_tile = HALO && tile < a.halo.n_push_tiles;      // warp-uniform
+    const bool halo_tile = HALO && tile < a.halo.n_wait_tiles;      // rows may read halo columns
     const float* __restrict__ xc_tile = xg + r0 * NS;
     float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
     float* __restrict__ r_tile = a.r + r0 * NS + c0;
@@ -322,45 +366,25 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
       const int off = lr * NS;
       const int jb = sm_ptr[lr] - a0;
       const int je = sm_ptr[lr + 1] - a0;
-      const unsigned span = unsigned(je - jb);
       const float4 xc = ldg_f4(xc_tile + off);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      // The slab offset a0 is a multiple of 4, so groups of four CSR entries are
-      // 16-byte aligned in shared memory: one LDS.128 brings four column indices,
-      // one four weights.  Slots outside [jb, je) (row head / tail) are predicated
-      // off, so the sum runs over the row's entries in stored order.
-      for (int jj = jb & ~3; jj < je; jj += 4) {
-        const int4 c4 = *reinterpret_cast<const int4*>(sm_col + jj);
-        const float4 w4 = *reinterpret_cast<const float4*>(sm_val + jj);
-        float4 xv[4];
-        bool ok[4];
-        const int base = jj - jb;
-        ok[0] = unsigned(base + 0) < span;
-        ok[1] = unsigned(base + 1) < span;
-        ok[2] = unsigned(base + 2) < span;
-        ok[3] = unsigned(base + 3) < span;
-        const int cq[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (ok[q]) xv[q] = gather_f4<HALO>(xg, cq[q], NS, n_owned);
-        const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (ok[q]) {
-            acc.x = fmaf(wq[q], xv[q].x, acc.x);
-            acc.y = fmaf(wq[q], xv[q].y, acc.y);
-            acc.z = fmaf(wq[q], xv[q].z, acc.z);
-            acc.w = fmaf(wq[q], xv[q].w, acc.w);
-          }
-        }
+      // direct mode: this row's x_old and first r / source packet are requested now (streaming
+      // loads, no L1 allocation) and consumed after the gather loop, which hides their latency
+      float4 xo_d = make_float4(0.f, 0.f, 0.f, 0.f), r0_d = xo_d;
+      if (!FIRST && VD) {
+        xo_d = __ldcs(reinterpret_cast<const float4*>(a.x_old + (r0 + lr) * NS + c0));
+        if (NSC != 0 && nscales > 0)
+          r0_d = __ldcs(reinterpret_cast<const float4*>(a.r + (r0 + lr) * NS + c0));
       }
+      const float4 acc = (HALO && halo_tile)
+                             ? row_gather_sum<NS, true>(sm_col, sm_val, jb, je, xg, n_owned)
+                             : row_gather_sum<NS, false>(sm_col, sm_val, jb, je, xg, n_owned);
       float4 xn;
       xn.x = fmaf(alpha, acc.x, beta * xc.x);
       xn.y = fmaf(alpha, acc.y, beta * xc.y);
       xn.z = fmaf(alpha, acc.z, beta * xc.z);
       xn.w = fmaf(alpha, acc.w, beta * xc.w);
       if (!FIRST) {
-        const float4 xo = *reinterpret_cast<const float4*>(sm_vec + off + c0);
+        const float4 xo = VD ? xo_d : *reinterpret_cast<const float4*>(sm_vec + off + c0);
         xn.x = fmaf(gamma, xo.x, xn.x);
         xn.y = fmaf(gamma, xo.y, xn.y);
         xn.z = fmaf(gamma, xo.z, xn.z);
@@ -372,7 +396,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
         for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
           if (NSC < 0 && i >= nscales) break;
           const float4 sv =
-              *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
+              VD ? (i == 0 ? r0_d
+                           : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
+                                                                    (r0 + lr) * NS + c0)))
+                 : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
           const float w = a.ck[i];
           xn.x = fmaf(w, sv.x, xn.x);
           xn.y = fmaf(w, sv.y, xn.y);
@@ -409,7 +436,10 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
           rv.z = fmaf(ck, xn.z, h0 * xc.z);
           rv.w = fmaf(ck, xn.w, h0 * xc.w);
         } else {
-          rv = *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
+          rv = VD ? (i == 0 ? r0_d
+                            : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
+                                                                     (r0 + lr) * NS + c0)))
+                  : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
           rv.x = fmaf(ck, xn.x, rv.x);
           rv.y = fmaf(ck, xn.y, rv.y);
           rv.z = fmaf(ck, xn.z, rv.z);
@@ -500,8 +530,9 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   const int warps = std::min(16, std::max(1, env_int("GSPB200_TILE_NW", 16)));
   // keep a CTA's ring within ~100 KB so that L1 keeps room for the x_cur gather
   const int budget = env_int("GSPB200_TILE_SMEM", 100 * 1024);
-  TileLayout lay(R, cap, (int)nsig, nscales, false, stages);
-  while (stages > 2 && lay.total(stages) > budget) { --stages; lay = TileLayout(R, cap, (int)nsig, nscales, false, stages); }
+  const bool vd = env_int("GSPB200_TILE_VDIR", 0) != 0;     // vectors not staged: small stages
+  TileLayout lay(R, cap, (int)nsig, nscales, vd, stages);
+  while (stages > 2 && lay.total(stages) > budget) { --stages; lay = TileLayout(R, cap, (int)nsig, nscales, vd, stages); }
   if (lay.total(stages) > 200 * 1024) return GSP_OK;        // heavy rows: row-group kernel
   plan->rows_per_tile = R;
   plan->slab_capacity = cap;
@@ -514,7 +545,8 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
 
 template <int G, int NSC, bool HALO>
 static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
-  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first, a.stages);
+  const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first || a.vec_direct,
+                       a.stages);
   const int smem = lay.total(a.stages);
   const int threads = 32 * (1 + a.consumer_warps);
   auto kern = first ? cheby_step_tiled<G, true, NSC, HALO> : cheby_step_tiled<G, false, NSC, HALO>;
@@ -555,6 +587,7 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          const int64_t* out_perm) {
   TileArgs a;
   a.out_perm = out_perm;
+  a.vec_direct = (!first && env_int("GSPB200_TILE_VDIR", add_source ? 1 : 0)) ? 1 : 0;
   a.keep_writes = env_int("GSPB200_TILE_REV", 1);
   a.reverse = (reverse && a.keep_writes) ? 1 : 0;
   a.add_source = add_source ? 1 : 0;

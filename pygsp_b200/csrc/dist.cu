@@ -12,6 +12,8 @@
 //   base+2      halo of T_0 (the input block) is in place
 //   base+2+s    halo of the block written by step s is in place, s = 1 .. K-1
 #include <type_traits>
+#include <vector>
+#include <cstdio>
 #include "common.cuh"
 #include "gspb200.h"
 
@@ -99,6 +101,36 @@ static int dist_step(const gsp_dist_plan* p, const gsp_tile_plan* tile, bool fus
   return GSP_OK;
 }
 
+// GSPB200_DIST_TRACE=1: per-step CUDA-event times of one call on stderr (diagnosis; synchronises)
+struct StepTrace {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  explicit StepTrace(cudaStream_t s) : st(s) {
+    const char* v = getenv("GSPB200_DIST_TRACE");
+    on = v && *v == '1';
+  }
+  void mark() {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+  }
+  ~StepTrace() {
+    if (!on || ev.size() < 2) return;
+    cudaEventSynchronize(ev.back());
+    fprintf(stderr, "[gspb200 dist trace] ms between marks:");
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %.3f", ms);
+    }
+    fprintf(stderr, "\n");
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+
 template <typename T>
 int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax, const double* c,
                   int nscales, int m, const T* x, int64_t nsig64, T* r, int clenshaw,
@@ -121,6 +153,8 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
       std::max(p->n_push_rows, p->n_boundary_rows) <= (n / tile->rows_per_tile) * tile->rows_per_tile;
   if (clenshaw && (nscales != 1 || K < 2 || !buf[2])) clenshaw = 0;
 
+  StepTrace trace(st);
+  trace.mark();
   // entry barrier, input block, halo of T_0
   int rc = DistTraits<T>::push(p, 0, 0, base + 1, nsig, stream);
   if (rc != GSP_OK) return rc;
@@ -135,6 +169,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
   }
   rc = DistTraits<T>::push(p, p->n_send, 0, base + 2, nsig, stream);
   if (rc != GSP_OK) return rc;
+  trace.mark();
 
   double ck[16], c0[16], zero[16];
   for (int i = 0; i < 16; ++i) zero[i] = 0;
@@ -158,6 +193,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
                         first ? -1.0 : -2.0, first ? 0.0 : -1.0, false, (k & 1) == 0,
                         base + 1 + k, base + 2 + k, k < K, stream);
       if (rc != GSP_OK) { if (r != r_out) cudaFreeAsync(r, st); return rc; }
+      trace.mark();
       std::swap(cur, old);
     }
     if (r != r_out) {
@@ -175,6 +211,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
                     c[K] * a2, c[K - 1] - 2.0 * c[K], 0.0, false, false, base + 2, base + 3, true,
                     stream);
   if (rc != GSP_OK) return rc;
+  trace.mark();
   int cur = 1, old = -1, step = 1;
   for (int k = K - 2; k >= 0; --k) {
     ++step;
@@ -193,6 +230,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
                       ck, zero, last ? 0.5 * a2 : a2, last ? -1.0 : -2.0, gamma, true, (k & 1) == 0,
                       base + 1 + step, base + 2 + step, !last, stream, last ? perm : nullptr);
     if (rc != GSP_OK) return rc;
+    trace.mark();
     old = cur;
     cur = dst;
   }

@@ -65,14 +65,110 @@ __global__ void lanczos_seed_kernel(int64_t n, T* v, uint64_t seed, double* part
 }
 
 // ------------------------------------------------------------------ SpMV
-// y = scale * (A x) with LPR lanes per row (LPR = 2..32, chosen from the mean row length):
-// the lanes of a row read consecutive CSR entries -- neighbouring rows' entries are
-// neighbours in memory, so a warp's accesses to indices / data are contiguous -- gather
-// x[col], and the row sum is reduced with warp shuffles (graph.py:911-917 spends its time
-// in exactly this product).  Optionally the kernel also leaves, per block, the partial sum
-// of y_i * (scale * x_i): the Lanczos alpha = v' L v comes out of the same pass.
-// scale = 1 / sqrt(sum(inv_norm2_parts)) when inv_norm2_parts is given (the vector x is
-// the unnormalised Lanczos vector u_j, see lanczos_run), else 1.
+// y = scale * (A x), LPR lanes per row (LPR = the power of two >= the mean row length, 2..32,
+// so that a row is normally ONE coalesced read of its entries and neighbouring rows' entries
+// -- neighbours in memory -- share 128-byte lines), row sums reduced with warp shuffles
+// (graph.py:911-917 spends its time in exactly this product).
+//
+// What bounded the first version (ncu: 51 us for N = 1e6, nnz = 1.2e7 = 0.33 of HBM) was not
+// DRAM but the L1 tag stage: a warp's 32 scalar gathers x[col] touch ~16 different lines.  So a
+// block owns a TILE of TR consecutive rows and keeps x[tile] and indptr[tile] in shared
+// memory: with a locality-preserving vertex numbering (Morton) ~90 % of a row's neighbours
+// lie inside its own tile and are served from shared memory (conflict-limited, a few cycles per
+// warp); the others take the global path.  U rows per lane group are in flight at once (a row
+// is a dependent chain entry -> x[col]).
+//
+// Optionally the kernel leaves, per block, the partial sum of y_i * (scale * x_i): the Lanczos
+// alpha = v' L v comes out of the same pass.  scale = 1 / sqrt(sum(inv_norm2_parts)) when
+// inv_norm2_parts is given (x is then the unnormalised Lanczos vector u_j), else 1.
+constexpr int kSpmvTileRows = 1024;
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kVecThreads)
+spmv_window_kernel(int64_t n, const int32_t* __restrict__ indptr,
+                   const int32_t* __restrict__ indices, const T* __restrict__ vals,
+                   const T* __restrict__ x, T* __restrict__ y, const double* norm2_parts,
+                   int n_parts, double* beta_out, double* dot_parts, int tile_rows) {
+  __shared__ T xs[kSpmvTileRows];
+  __shared__ int32_t ps[kSpmvTileRows + 1];
+  double scale = 1.0;
+  if (norm2_parts) {
+    const double nb = sqrt(sum_partials(norm2_parts, n_parts));
+    scale = nb > 0 ? 1.0 / nb : 0.0;
+    if (beta_out && blockIdx.x == 0 && threadIdx.x == 0) *beta_out = nb;
+  }
+  constexpr int RPB = kVecThreads / LPR;          // rows per block and pass
+  constexpr int U = 4;                            // independent rows per lane group and trip
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  double dot = 0;
+  const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * tile_rows;
+    const int rows = (n - r0 < int64_t(tile_rows)) ? int(n - r0) : tile_rows;
+    __syncthreads();                               // the previous tile's window is no longer read
+    for (int i = threadIdx.x; i <= rows; i += kVecThreads) {
+      ps[i] = __ldg(indptr + r0 + i);
+      if (i < rows) xs[i] = __ldg(x + r0 + i);
+    }
+    __syncthreads();
+    for (int base = 0; base < rows; base += RPB * U) {   // uniform trip count over the block
+      double acc[U];
+      int jn[U], je[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {                // first entry of U rows: loads issued together
+        const int lr = base + u * RPB + sub;
+        acc[u] = 0;
+        jn[u] = je[u] = 0;
+        int col = -1;
+        T val = T(0);
+        if (lr < rows) {
+          const int j = ps[lr] + lane;
+          je[u] = ps[lr + 1];
+          jn[u] = j + LPR;
+          if (j < je[u]) {
+            col = __ldg(indices + j);
+            val = __ldg(vals + j);
+          }
+        }
+        if (col >= 0) {
+          const unsigned off = unsigned(col - int(r0));   // int: n < 2^31 rows per block of L
+          const T xv = (int64_t(col) >= r0 && off < unsigned(rows)) ? xs[off] : __ldg(x + col);
+          acc[u] = double(val) * double(xv);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {                // rows longer than LPR entries
+        for (int j = jn[u]; j < je[u]; j += LPR) {
+          const int col = __ldg(indices + j);
+          const unsigned off = unsigned(col - int(r0));
+          const T xv = (int64_t(col) >= r0 && off < unsigned(rows)) ? xs[off] : __ldg(x + col);
+          acc[u] += double(__ldg(vals + j)) * double(xv);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double a = acc[u];
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o, LPR);
+        const int lr = base + u * RPB + sub;
+        if (lr < rows && lane == 0) {
+          const double yi = a * scale;
+          y[r0 + lr] = T(yi);
+          if (dot_parts) dot += double(T(yi)) * (double(xs[lr]) * scale);
+        }
+      }
+    }
+  }
+  if (dot_parts) {                                 // uniform branch
+    dot = block_allreduce(dot);
+    if (threadIdx.x == 0) dot_parts[blockIdx.x] = dot;
+  }
+}
+
+// The first form of the product (no shared-memory window): LPR = the largest power of two <=
+// the mean row length, every lane group walks its row in steps of LPR.  Kept selectable
+// (GSPB200_SPMV=subwarp) for A/B measurements and for numberings without locality.
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kVecThreads)
 spmv_subwarp_kernel(int64_t n, const int32_t* __restrict__ indptr,
@@ -143,30 +239,69 @@ spmv_subwarp_kernel(int64_t n, const int32_t* __restrict__ indptr,
   }
 }
 
-static inline int spmv_lanes(int64_t n, int64_t nnz) {
+static inline int spmv_lanes_subwarp(int64_t n, int64_t nnz) {
   const double mean = n > 0 ? double(nnz) / double(n) : 1.0;
   int lpr = 2;
-  while (lpr < 32 && 2 * lpr <= mean) lpr *= 2;      // largest power of two <= mean, in [2, 32]
+  while (lpr < 32 && 2 * lpr <= mean) lpr *= 2;
   return lpr;
 }
 
-static inline int spmv_blocks(int64_t n, int lpr) {
-  const int64_t rpb = (kVecThreads / lpr) * 4;        // U = 4 rows per lane group and trip
+static inline int spmv_lanes(int64_t n, int64_t nnz) {
+  const double mean = n > 0 ? double(nnz) / double(n) : 1.0;
+  int lpr = 2;
+  while (lpr < 32 && lpr < mean) lpr *= 2;           // smallest power of two >= mean, in [2, 32]
+  return lpr;
+}
+
+// rows per tile: up to kSpmvTileRows, smaller when the matrix would otherwise leave SMs idle
+static inline int spmv_tile_rows(int64_t n) {
+  const char* e = getenv("GSPB200_SPMV_TR");
+  if (e && atoi(e) >= 32 && atoi(e) <= kSpmvTileRows) return atoi(e);
+  int tr = kSpmvTileRows;
+  while (tr > 128 && ceil_div(n, (int64_t)tr) < int64_t(sm_count()) * 4) tr /= 2;
+  return tr;
+}
+
+static inline int spmv_blocks(int64_t n, int tile_rows) {
+  const int64_t tiles = ceil_div(n, (int64_t)tile_rows);
   return (int)std::max<int64_t>(
-      1, std::min<int64_t>(ceil_div(n, rpb), std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks)));
+      1, std::min<int64_t>(tiles, std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks)));
 }
 
 template <typename T>
 static int spmv_launch(int64_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                        const T* vals, const T* x, T* y, const double* norm2_parts, int n_parts,
                        double* beta_out, double* dot_parts, int* blocks_out, cudaStream_t st) {
-  const int lpr = spmv_lanes(n, nnz);
-  const int blocks = spmv_blocks(n, lpr);
-  if (blocks_out) *blocks_out = blocks;
-#define GSP_SPMV(L)                                                                          \
+  const char* form = getenv("GSPB200_SPMV");
+  if (form && strcmp(form, "subwarp") == 0) {
+    const int lpr = spmv_lanes_subwarp(n, nnz);
+    const int64_t rpb = (kVecThreads / lpr) * 4;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, rpb),
+        std::min<int64_t>(int64_t(sm_count()) * 8, kMaxVecBlocks)));
+    if (blocks_out) *blocks_out = blocks;
+#define GSP_SPMV_SW(L)                                                                       \
   spmv_subwarp_kernel<T, L><<<blocks, kVecThreads, 0, st>>>(n, indptr, indices, vals, x, y, \
                                                              norm2_parts, n_parts, beta_out, \
                                                              dot_parts)
+    switch (lpr) {
+      case 2: GSP_SPMV_SW(2); break;
+      case 4: GSP_SPMV_SW(4); break;
+      case 8: GSP_SPMV_SW(8); break;
+      case 16: GSP_SPMV_SW(16); break;
+      default: GSP_SPMV_SW(32); break;
+    }
+#undef GSP_SPMV_SW
+    GSP_LAUNCH_CHECK("spmv_subwarp");
+    return GSP_OK;
+  }
+  const int lpr = spmv_lanes(n, nnz);
+  const int tr = spmv_tile_rows(n);
+  const int blocks = spmv_blocks(n, tr);
+  if (blocks_out) *blocks_out = blocks;
+#define GSP_SPMV(L)                                                                         \
+  spmv_window_kernel<T, L><<<blocks, kVecThreads, 0, st>>>(n, indptr, indices, vals, x, y, \
+                                                            norm2_parts, n_parts, beta_out, \
+                                                            dot_parts, tr)
   switch (lpr) {
     case 2: GSP_SPMV(2); break;
     case 4: GSP_SPMV(4); break;
@@ -175,7 +310,7 @@ static int spmv_launch(int64_t n, int64_t nnz, const int32_t* indptr, const int3
     default: GSP_SPMV(32); break;
   }
 #undef GSP_SPMV
-  GSP_LAUNCH_CHECK("spmv_subwarp");
+  GSP_LAUNCH_CHECK("spmv_window");
   return GSP_OK;
 }
 

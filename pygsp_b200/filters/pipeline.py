@@ -24,6 +24,7 @@ from .. import _native as nat
 
 _TILED_WIDTHS = (128, 64, 32, 16, 8)
 _streams = {}
+last_trace = None      # GSPB200_E2E_TRACE=1: [(stage, chunk, start_ms, end_ms)] of the last call
 
 
 def _side_streams(device):
@@ -94,25 +95,44 @@ def run_pinned(compute, device, dtype, xh, nscales, out=None, chunks=None):
         main = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device)
         xin = [torch.empty((n, w), dtype=dtype, device=device) for _, w in chunks]
+        trace = os.environ.get("GSPB200_E2E_TRACE") == "1"
+        marks = []
+
+        def mark(stage, j, stream):
+            if trace:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks.append((stage, j, ev))
+        mark("t0", -1, main)
         s_in.wait_stream(main)
         s_out.wait_stream(main)
         ev_in = []
-        for (o, w), buf in zip(chunks, xin):           # uploads run back to back on their stream
+        for j, ((o, w), buf) in enumerate(zip(chunks, xin)):   # uploads run back to back on their stream
+            mark("up_begin", j, s_in)
             _copy2d(buf.data_ptr(), w * item, xh.data_ptr() + o * item, nsig * item, w * item, n, 1,
                     s_in, use_kernel)
             ev_in.append(s_in.record_event())
+            mark("up_end", j, s_in)
         results = []
         for j, (o, w) in enumerate(chunks):
             main.wait_event(ev_in[j])
+            mark("compute_begin", j, main)
             res = compute(xin[j])
             results.append(res)
+            mark("compute_end", j, main)
             s_out.wait_event(main.record_event())
+            mark("down_begin", j, s_out)
             for i in range(nscales):
                 _copy2d(out[i].data_ptr() + o * item, nsig * item, res[i].data_ptr(), w * item,
                         w * item, n, 2, s_out, use_kernel)
+            mark("down_end", j, s_out)
         main.wait_stream(s_in)
         main.wait_stream(s_out)
         main.synchronize()                     # a host result must be complete on return
+        if trace:
+            global last_trace
+            t0 = marks[0][2]
+            last_trace = [(stage, j, round(t0.elapsed_time(ev), 3)) for stage, j, ev in marks[1:]]
     return out
 
 

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--order", type=int, default=30)
     ap.add_argument("--rounds", type=int, default=5)
     ap.add_argument("--calls", type=int, default=10)
+    ap.add_argument("--k", type=int, default=10)
     ap.add_argument("variants", nargs="*",
                     default=["forward", "clenshaw", "clenshaw:TILE_REV=0", "forward:TILE_REV=0",
                              "clenshaw:TILE_HINT=0"])
@@ -34,7 +35,7 @@ def main():
     import pygsp_b200 as gsp
     from pygsp_b200.filters import approximations as apx
 
-    G = gsp.graphs.Sensor(a.n, k=10, seed=0, order="morton")
+    G = gsp.graphs.Sensor(a.n, k=a.k, seed=0, order="morton")
     G.estimate_lmax()
     g = gsp.filters.Heat(G, scale=50)
     c = np.atleast_2d(gsp.filters.compute_cheby_coeff(g, m=a.order))
@@ -50,14 +51,19 @@ def main():
             apx.cheby_clenshaw_device(G.L, G.lmax, c, x, out=out[0], work=work)
 
     results = {v: [] for v in a.variants}
+    reference, equal = {}, {}
     for rnd in range(a.rounds + 1):                     # round 0 = warm-up
         for v in a.variants:
             form, _, env = v.partition(":")
             sets = dict(kv.split("=") for kv in env.split(",") if kv)
             for k, val in sets.items():
                 os.environ["GSPB200_" + k] = val
+            G.L._plans.clear()                        # the tiling reads the toggles too
             run(form)
             torch.cuda.synchronize()
+            if rnd == 0:                              # every variant must give the form's bits
+                got = (out[0] if form != "forward" else out).clone()
+                equal[v] = bool(torch.equal(got, reference.setdefault(form, got)))
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(a.calls):
@@ -73,6 +79,7 @@ def main():
         _, _, b = bench.algorithmic_bytes(G.N, G.L.nnz, a.nsig, 1, a.order, clenshaw=form != "forward")
         best = min(ms)
         print(json.dumps({"variant": v, "ms_per_call_rounds": [round(t, 3) for t in ms],
+                          "bit_identical_to_first_variant_of_form": equal.get(v),
                           "best_ms": round(best, 3), "frac_best": round(b / best / 1e6 / peak, 3),
                           "units_per_s_best": G.N * a.nsig * a.order / best * 1e3}), flush=True)
 
