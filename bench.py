@@ -588,6 +588,9 @@ def run_ours(args):
         nnz_global = int(t.item())
     t_build = time.perf_counter() - t_build0
     clen = c.shape[0] == 1                           # the engine's default form for one filter
+    if op is not None and world > 1:                 # (the packed-NCCL exchange keeps the forward form)
+        clen = clen and op._exchange_mode(nsig) == "p2p" and \
+            os.environ.get("GSPB200_BENCH_CLENSHAW") != "0"
     # signals: one seeded global block, every rank takes its rows (strong scaling keeps the
     # whole block for the parity leg against the one-GPU engine)
     gen = torch.Generator(device="cuda").manual_seed(0 if G is not None else rank)

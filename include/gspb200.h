@@ -286,7 +286,7 @@ typedef struct gsp_dist_plan {
   uint64_t* flags;
   const int32_t* neighbor_ids;
   int32_t n_neighbors;
-  int32_t reserved;
+  int32_t separate_exchange; /* != 0: never fuse the exchange into the step kernel (wait / step / push kernels) */
   uint32_t* push_counter;
   uint64_t* fused_counter;
   int64_t n_send;

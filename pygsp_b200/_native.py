@@ -51,7 +51,7 @@ class DistPlan(ctypes.Structure):
                 ("buf", ctypes.c_void_p * 3), ("peer_base", ctypes.c_void_p * 3),
                 ("peer_flags", ctypes.c_void_p), ("flags", ctypes.c_void_p),
                 ("neighbor_ids", ctypes.c_void_p), ("n_neighbors", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("push_counter", ctypes.c_void_p),
+                ("separate_exchange", ctypes.c_int32), ("push_counter", ctypes.c_void_p),
                 ("fused_counter", ctypes.c_void_p), ("n_send", ctypes.c_int64),
                 ("src_row", ctypes.c_void_p), ("dst_peer", ctypes.c_void_p),
                 ("dst_row", ctypes.c_void_p), ("n_push_rows", ctypes.c_int64),

@@ -158,14 +158,15 @@ __device__ __forceinline__ int64_t tile_of_slot(const TileArgs& a, int64_t slot)
   return a.reverse ? a.n_tiles - 1 - (slot - a.n_front) : slot;
 }
 
-// halo rows of x_cur are written by the neighbours (peer stores) while this kernel may
-// already be running: they are read through L2 (ld.global.cg), never through the
-// non-coherent path.  Rows this GPU owns are read-only for the whole launch: ld.global.nc.
-template <bool HALO>
-__device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int col, int ns,
-                                            int n_owned) {
+// Halo rows of x_cur are written by the neighbours (peer stores) while this kernel may
+// already be running: a tile whose rows reference halo columns (the boundary tiles of a
+// partitioned step, a few per launch) gathers through L2 (ld.global.cg), never through the
+// non-coherent path.  Interior tiles only touch rows this GPU owns, which are read-only for the
+// whole launch: ld.global.nc.
+template <bool COH>
+__device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int col, int ns) {
   const float* p = xg + int64_t(col) * ns;
-  if (HALO && col >= n_owned) return __ldcg(reinterpret_cast<const float4*>(p));
+  if (COH) return __ldcg(reinterpret_cast<const float4*>(p));
   return ldg_f4(p);
 }
 
@@ -178,7 +179,7 @@ __device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int co
 template <int NS, bool COH>
 __device__ __forceinline__ float4 row_gather_sum(const int32_t* __restrict__ sm_col,
                                                  const float* __restrict__ sm_val, int jb, int je,
-                                                 const float* __restrict__ xg, int n_owned) {
+                                                 const float* __restrict__ xg) {
   const unsigned span = unsigned(je - jb);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int jj = jb & ~3; jj < je; jj += 4) {
@@ -194,7 +195,7 @@ __device__ __forceinline__ float4 row_gather_sum(const int32_t* __restrict__ sm_
     const int cq[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (ok[q]) xv[q] = gather_f4<COH>(xg, cq[q], NS, n_owned);
+      if (ok[q]) xv[q] = gather_f4<COH>(xg, cq[q], NS);
     const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -207,6 +208,181 @@ __device__ __forceinline__ float4 row_gather_sum(const int32_t* __restrict__ sm_
     }
   }
   return acc;
+}
+
+// What a consumer lane needs to process one staged tile.
+struct TileCtx {
+  const float* sm_vec;      // x_old tile, then one r / source tile per scale (empty in direct mode)
+  const int32_t* sm_col;    // CSR slab: column indices
+  const float* sm_val;      //           values
+  const int32_t* sm_ptr;    // indptr[r0 .. r0 + R], slab offset at [R + 4]
+  int64_t tile;
+  int64_t r0;               // first row of the tile (block-local row index)
+  int cw, sub, c0;          // consumer warp, row slot inside the warp, first column of the lane
+  bool vd;                  // direct mode: x_old / r rows come straight from global memory
+};
+
+// The rows of one tile: gather + three-term recurrence + coefficient AXPYs + stores.
+// COH: the tile's rows may reference halo columns (coherent gathers through L2).
+template <int G, bool FIRST, int NSC, bool COH>
+__device__ __forceinline__ void tile_rows(const TileArgs& a, const TileCtx t) {
+  constexpr int RP = 32 / G;               // rows in flight per warp
+  constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
+  const int R = a.rows_per_tile;
+  const int NW = a.consumer_warps;
+  const int c0 = t.c0;
+  const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
+  const int nscales = NSC >= 0 ? NSC : a.nscales;
+  const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
+  const bool keep_writes = a.keep_writes != 0;
+  const bool VD = t.vd;
+  const float* sm_vec = t.sm_vec;
+  const int a0 = t.sm_ptr[R + 4];
+  const int64_t r0 = t.r0;
+  const float* __restrict__ xc_tile = xg + r0 * NS;
+  float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
+  float* __restrict__ r_tile = a.r + r0 * NS + c0;
+  const int64_t r_stride = a.r_rows * NS;
+
+  for (int lr = t.cw * RP + t.sub; lr < R; lr += NW * RP) {
+    const int off = lr * NS;
+    const int jb = t.sm_ptr[lr] - a0;
+    const int je = t.sm_ptr[lr + 1] - a0;
+    const float4 xc = ldg_f4(xc_tile + off);
+    // direct mode: this row's x_old and first r / source packet are requested now (streaming
+    // loads, no L1 allocation) and consumed after the gather loop, which hides their latency
+    float4 xo_d = make_float4(0.f, 0.f, 0.f, 0.f), r0_d = xo_d;
+    if (!FIRST && VD) {
+      xo_d = __ldcs(reinterpret_cast<const float4*>(a.x_old + (r0 + lr) * NS + c0));
+      if (NSC != 0 && nscales > 0)
+        r0_d = __ldcs(reinterpret_cast<const float4*>(a.r + (r0 + lr) * NS + c0));
+    }
+    const float4 acc = row_gather_sum<NS, COH>(t.sm_col, t.sm_val, jb, je, xg);
+    float4 xn;
+    xn.x = fmaf(alpha, acc.x, beta * xc.x);
+    xn.y = fmaf(alpha, acc.y, beta * xc.y);
+    xn.z = fmaf(alpha, acc.z, beta * xc.z);
+    xn.w = fmaf(alpha, acc.w, beta * xc.w);
+    if (!FIRST) {
+      const float4 xo = VD ? xo_d : *reinterpret_cast<const float4*>(sm_vec + off + c0);
+      xn.x = fmaf(gamma, xo.x, xn.x);
+      xn.y = fmaf(gamma, xo.y, xn.y);
+      xn.z = fmaf(gamma, xo.z, xn.z);
+      xn.w = fmaf(gamma, xo.w, xn.w);
+    }
+    if (!FIRST && NSC != 0 && a.add_source) {
+      // Clenshaw form: the r tiles are read-only source blocks, x_new += sum_i ck_i s_i
+#pragma unroll
+      for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
+        if (NSC < 0 && i >= nscales) break;
+        const float4 sv =
+            VD ? (i == 0 ? r0_d
+                         : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
+                                                                  (r0 + lr) * NS + c0)))
+               : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
+        const float w = a.ck[i];
+        xn.x = fmaf(w, sv.x, xn.x);
+        xn.y = fmaf(w, sv.y, xn.y);
+        xn.z = fmaf(w, sv.z, xn.z);
+        xn.w = fmaf(w, sv.w, xn.w);
+      }
+    }
+    if (a.out_perm)      // the caller's row order: local row -> original row (uniform branch)
+      store_f4(a.x_new + __ldg(a.out_perm + r0 + lr) * NS + c0, xn, keep_writes);
+    else
+      store_f4(xn_tile + off, xn, keep_writes);
+#pragma unroll
+    for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
+      if (NSC < 0 && i >= nscales) break;
+      if (!FIRST && a.add_source) break;
+      float4 rv;
+      const float ck = a.ck[i];
+      if (FIRST) {
+        const float h0 = a.half_c0[i];
+        rv.x = fmaf(ck, xn.x, h0 * xc.x);
+        rv.y = fmaf(ck, xn.y, h0 * xc.y);
+        rv.z = fmaf(ck, xn.z, h0 * xc.z);
+        rv.w = fmaf(ck, xn.w, h0 * xc.w);
+      } else {
+        rv = VD ? (i == 0 ? r0_d
+                          : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
+                                                                   (r0 + lr) * NS + c0)))
+                : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
+        rv.x = fmaf(ck, xn.x, rv.x);
+        rv.y = fmaf(ck, xn.y, rv.y);
+        rv.z = fmaf(ck, xn.z, rv.z);
+        rv.w = fmaf(ck, xn.w, rv.w);
+      }
+      store_f4(r_tile + i * r_stride + off, rv, keep_writes);
+    }
+  }
+}
+
+// A boundary ("front") tile of a partitioned step -- a few tiles per launch.  It is a real
+// function call on purpose: inlined, its extra state (flags, peer tables, a second copy of
+// the gather loop) made ptxas spill registers in the interior tiles' loop as well
+// (1.6 x slower steps, measured).  Does, for one consumer warp:
+//   wait   : until the neighbours have published the halo of x_cur (they stored it straight
+//            into this GPU's memory and released wait_value afterwards);
+//   rows   : the tile's rows with coherent gathers;
+//   push   : every lane re-reads the packets it has just stored (its own writes, program
+//            order) and stores them into the halo rows of the neighbours that reference the
+//            row -- peer stores over NVLink;
+//   publish: every warp of every CTA checks in once per front tile; when the last one has,
+//            (a) all boundary rows of x_new are stored in the neighbours and (b) nobody on this
+//            GPU reads the halo of x_cur any more: the step is released to the neighbours,
+//            which may then read their halo of x_new and overwrite our halo of x_cur's buffer.
+template <int G, bool FIRST, int NSC>
+__device__ __noinline__ void boundary_tile(const TileArgs& a, const TileCtx t, int lane) {
+  constexpr int RP = 32 / G;
+  constexpr int NS = 4 * G;
+  const int R = a.rows_per_tile;
+  const int NW = a.consumer_warps;
+  if (t.tile < a.halo.n_wait_tiles && a.halo.n_wait > 0) {
+    if (lane < a.halo.n_wait) {
+      const unsigned long long* f =
+          reinterpret_cast<const unsigned long long*>(a.halo.wait_flags) + a.halo.wait_ids[lane];
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+      } while (seen < a.halo.wait_value);
+    }
+    __syncwarp();
+  }
+  tile_rows<G, FIRST, NSC, true>(a, t);
+  if (t.tile >= a.halo.n_push_tiles) return;
+  if (!a.out_perm) {
+    const float* xn_tile = a.x_new + t.r0 * NS + t.c0;
+    for (int lr = t.cw * RP + t.sub; lr < R; lr += NW * RP) {
+      const int64_t lrow = t.tile * R + lr;
+      if (lrow >= a.halo.n_push_rows) continue;
+      const int e0 = a.halo.push_ptr[lrow], e1 = a.halo.push_ptr[lrow + 1];
+      if (e0 == e1) continue;
+      const float4 xn = *reinterpret_cast<const float4*>(xn_tile + lr * NS);
+      for (int e = e0; e < e1; ++e) {
+        float* dst = reinterpret_cast<float* const*>(a.halo.peer_base)[a.halo.push_peer[e]] +
+                     a.halo.push_row[e] * NS + t.c0;
+        *reinterpret_cast<float4*>(dst) = xn;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned long long want =
+        (unsigned long long)a.halo.n_push_tiles * (unsigned long long)NW;
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.halo.push_counter), 1ull);
+    if (prev + 1 == want) {
+      *reinterpret_cast<volatile unsigned long long*>(a.halo.push_counter) = 0ull;
+      __threadfence_system();
+      for (int q = 0; q < a.halo.n_neighbors; ++q)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(
+                         reinterpret_cast<unsigned long long* const*>(a.halo.peer_flags)[q]),
+                     "l"((unsigned long long)a.halo.publish_value)
+                     : "memory");
+    }
+  }
 }
 
 template <int G, bool FIRST, int NSC, bool HALO>
@@ -315,162 +491,27 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
   }
 
   // ---------------------------------------------------------------- consumers
-  constexpr int RP = 32 / G;               // rows in flight per warp
   const int cw = warp - 1;
-  constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
   const int sub = lane / G;
   const int c0 = (lane % G) * 4;
-  const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
-  const int nscales = NSC >= 0 ? NSC : a.nscales;
-  const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
-  const bool keep_writes = a.keep_writes != 0;
-  const int n_owned = HALO ? int(a.halo.n_owned) : 0;
-  bool halo_seen = !(HALO && a.halo.n_wait > 0);
   int it = 0;
   for (int64_t slot = blockIdx.x; slot < a.n_tiles; slot += gridDim.x, ++it) {
     const int64_t tile = tile_of_slot(a, slot);
     const int s = it % S;
     const uint32_t round = uint32_t(it / S);
-    if (HALO && !halo_seen && tile < a.halo.n_wait_tiles) {
-      // First tile of this warp whose rows reference halo columns: the neighbours must have
-      // published the halo of x_cur (they stored it straight into this GPU's memory and
-      // released wait_value afterwards).  Interior tiles never come here, so a CTA that
-      // owns interior tiles only does not wait at all.
-      if (lane < a.halo.n_wait) {
-        const unsigned long long* f =
-            reinterpret_cast<const unsigned long long*>(a.halo.wait_flags) + a.halo.wait_ids[lane];
-        unsigned long long seen;
-        do {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-        } while (seen < a.halo.wait_value);
-      }
-      __syncwarp();
-      halo_seen = true;
-    }
     mbar_wait(full + s, round & 1u);
     unsigned char* st = stage0 + size_t(s) * lay.stage_bytes;
-    const float* sm_vec = reinterpret_cast<const float*>(st);
-    const int32_t* sm_col = reinterpret_cast<const int32_t*>(st + lay.vec_bytes);
-    const float* sm_val = reinterpret_cast<const float*>(st + lay.vec_bytes + lay.slab_bytes);
-    int32_t* sm_ptr = reinterpret_cast<int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes);
-    const int a0 = sm_ptr[R + 4];
-    const int64_t r0 = a.row_begin + tile * R;
-    const bool push_tile = HALO && tile < a.halo.n_push_tiles;      // warp-uniform
-    const bool halo_tile = HALO && tile < a.halo.n_wait_tiles;      // rows may read halo columns
-    const float* __restrict__ xc_tile = xg + r0 * NS;
-    float* __restrict__ xn_tile = a.x_new + r0 * NS + c0;
-    float* __restrict__ r_tile = a.r + r0 * NS + c0;
-    const int64_t r_stride = a.r_rows * NS;
-
-    for (int lr = cw * RP + sub; lr < R; lr += NW * RP) {
-      const int off = lr * NS;
-      const int jb = sm_ptr[lr] - a0;
-      const int je = sm_ptr[lr + 1] - a0;
-      const float4 xc = ldg_f4(xc_tile + off);
-      // direct mode: this row's x_old and first r / source packet are requested now (streaming
-      // loads, no L1 allocation) and consumed after the gather loop, which hides their latency
-      float4 xo_d = make_float4(0.f, 0.f, 0.f, 0.f), r0_d = xo_d;
-      if (!FIRST && VD) {
-        xo_d = __ldcs(reinterpret_cast<const float4*>(a.x_old + (r0 + lr) * NS + c0));
-        if (NSC != 0 && nscales > 0)
-          r0_d = __ldcs(reinterpret_cast<const float4*>(a.r + (r0 + lr) * NS + c0));
-      }
-      const float4 acc = (HALO && halo_tile)
-                             ? row_gather_sum<NS, true>(sm_col, sm_val, jb, je, xg, n_owned)
-                             : row_gather_sum<NS, false>(sm_col, sm_val, jb, je, xg, n_owned);
-      float4 xn;
-      xn.x = fmaf(alpha, acc.x, beta * xc.x);
-      xn.y = fmaf(alpha, acc.y, beta * xc.y);
-      xn.z = fmaf(alpha, acc.z, beta * xc.z);
-      xn.w = fmaf(alpha, acc.w, beta * xc.w);
-      if (!FIRST) {
-        const float4 xo = VD ? xo_d : *reinterpret_cast<const float4*>(sm_vec + off + c0);
-        xn.x = fmaf(gamma, xo.x, xn.x);
-        xn.y = fmaf(gamma, xo.y, xn.y);
-        xn.z = fmaf(gamma, xo.z, xn.z);
-        xn.w = fmaf(gamma, xo.w, xn.w);
-      }
-      if (!FIRST && NSC != 0 && a.add_source) {
-        // Clenshaw form: the r tiles are read-only source blocks, x_new += sum_i ck_i s_i
-#pragma unroll
-        for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
-          if (NSC < 0 && i >= nscales) break;
-          const float4 sv =
-              VD ? (i == 0 ? r0_d
-                           : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
-                                                                    (r0 + lr) * NS + c0)))
-                 : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
-          const float w = a.ck[i];
-          xn.x = fmaf(w, sv.x, xn.x);
-          xn.y = fmaf(w, sv.y, xn.y);
-          xn.z = fmaf(w, sv.z, xn.z);
-          xn.w = fmaf(w, sv.w, xn.w);
-        }
-      }
-      if (a.out_perm)      // the caller's row order: local row -> original row (uniform branch)
-        store_f4(a.x_new + __ldg(a.out_perm + r0 + lr) * NS + c0, xn, keep_writes);
-      else
-        store_f4(xn_tile + off, xn, keep_writes);
-      if (push_tile) {
-        // fused halo push: this row's new value goes straight into the halo rows of
-        // the neighbours that reference it (peer stores over NVLink)
-        const int64_t lrow = tile * R + lr;
-        if (lrow < a.halo.n_push_rows) {
-          for (int e = a.halo.push_ptr[lrow]; e < a.halo.push_ptr[lrow + 1]; ++e) {
-            float* dst = reinterpret_cast<float* const*>(a.halo.peer_base)[a.halo.push_peer[e]] +
-                         a.halo.push_row[e] * NS + c0;
-            *reinterpret_cast<float4*>(dst) = xn;
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
-        if (NSC < 0 && i >= nscales) break;
-        if (!FIRST && a.add_source) break;
-        float4 rv;
-        const float ck = a.ck[i];
-        if (FIRST) {
-          const float h0 = a.half_c0[i];
-          rv.x = fmaf(ck, xn.x, h0 * xc.x);
-          rv.y = fmaf(ck, xn.y, h0 * xc.y);
-          rv.z = fmaf(ck, xn.z, h0 * xc.z);
-          rv.w = fmaf(ck, xn.w, h0 * xc.w);
-        } else {
-          rv = VD ? (i == 0 ? r0_d
-                            : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
-                                                                     (r0 + lr) * NS + c0)))
-                  : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
-          rv.x = fmaf(ck, xn.x, rv.x);
-          rv.y = fmaf(ck, xn.y, rv.y);
-          rv.z = fmaf(ck, xn.z, rv.z);
-          rv.w = fmaf(ck, xn.w, rv.w);
-        }
-        store_f4(r_tile + i * r_stride + off, rv, keep_writes);
-      }
-    }
-    if (push_tile) {
-      // Every warp of every CTA checks in once per front tile.  When the last one has, (a) all
-      // boundary rows of x_new are stored in the neighbours and (b) nobody on this GPU reads
-      // the halo of x_cur any more (only front tiles do): publish the step.  The neighbours
-      // then may both read their halo of x_new and overwrite our halo of x_cur's buffer.
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        const unsigned long long want =
-            (unsigned long long)a.halo.n_push_tiles * (unsigned long long)NW;
-        const unsigned long long prev = atomicAdd(
-            reinterpret_cast<unsigned long long*>(a.halo.push_counter), 1ull);
-        if (prev + 1 == want) {
-          *reinterpret_cast<volatile unsigned long long*>(a.halo.push_counter) = 0ull;
-          __threadfence_system();
-          for (int q = 0; q < a.halo.n_neighbors; ++q)
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(
-                             reinterpret_cast<unsigned long long* const*>(a.halo.peer_flags)[q]),
-                         "l"((unsigned long long)a.halo.publish_value)
-                         : "memory");
-        }
-      }
-    }
+    // (the context is built per use and passed BY VALUE: a struct whose address escapes to the
+    //  non-inlined boundary routine would live in local memory for the interior path too)
+    const TileCtx t = {reinterpret_cast<const float*>(st),
+                       reinterpret_cast<const int32_t*>(st + lay.vec_bytes),
+                       reinterpret_cast<const float*>(st + lay.vec_bytes + lay.slab_bytes),
+                       reinterpret_cast<const int32_t*>(st + lay.vec_bytes + 2 * lay.slab_bytes),
+                       tile, a.row_begin + tile * R, cw, sub, c0, VD};
+    if (HALO && tile < a.n_front)          // warp-uniform; interior tiles never wait
+      boundary_tile<G, FIRST, NSC>(a, t, lane);
+    else
+      tile_rows<G, FIRST, NSC, false>(a, t);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
   }

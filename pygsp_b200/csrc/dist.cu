@@ -77,15 +77,36 @@ static int dist_step(const gsp_dist_plan* p, const gsp_tile_plan* tile, bool fus
     h.n_boundary_rows = p->n_boundary_rows;
     h.n_owned = n;
     h.publish = publish ? 1 : 0;
-    int64_t done = 0;
-    int rc = cheby_step_tiled_f32(first, 0, n, p->nnz, p->indptr, p->indices,
-                                  reinterpret_cast<const float*>(p->data),
-                                  reinterpret_cast<const float*>(x_cur),
-                                  reinterpret_cast<const float*>(x_old),
-                                  reinterpret_cast<float*>(x_new), reinterpret_cast<float*>(r),
-                                  r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, *tile, &h, &done,
-                                  st, add_source, reverse, out_perm);
+    // Two launches on the same stream.  (1) The boundary ("front") tiles with the
+    // halo-capable instantiation: wait for the neighbours' flags, coherent gathers, peer
+    // stores of the new boundary rows, publish.  (2) All interior tiles with the plain
+    // instantiation.  One kernel for both was 1.6 x slower per step: the boundary code's
+    // registers spilled inside the interior tiles' gather loop (ptxas, 60-register cap);
+    // the front launch is a few dozen tiles (~10 us) and publishes before the interior runs.
+    const int R = tile->rows_per_tile;
+    const int64_t front_rows =
+        ceil_div(std::max<int64_t>(publish ? p->n_push_rows : 0, p->n_boundary_rows), (int64_t)R) * R;
+    int64_t done = 0, done_front = 0;
+    int rc = GSP_OK;
+    if (front_rows > 0) {
+      rc = cheby_step_tiled_f32(first, 0, front_rows, p->nnz, p->indptr, p->indices,
+                                reinterpret_cast<const float*>(p->data),
+                                reinterpret_cast<const float*>(x_cur),
+                                reinterpret_cast<const float*>(x_old),
+                                reinterpret_cast<float*>(x_new), reinterpret_cast<float*>(r), r_rows,
+                                nsig, nscales, ck, c0, alpha, beta, gamma, *tile, &h, &done_front, st,
+                                add_source, false, out_perm);
+      if (rc != GSP_OK) return rc;
+      GSP_REQUIRE(done_front == front_rows, "front tiles must be whole tiles");
+    }
+    rc = cheby_step_tiled_f32(first, front_rows, n, p->nnz, p->indptr, p->indices,
+                              reinterpret_cast<const float*>(p->data),
+                              reinterpret_cast<const float*>(x_cur),
+                              reinterpret_cast<const float*>(x_old), reinterpret_cast<float*>(x_new),
+                              reinterpret_cast<float*>(r), r_rows, nsig, nscales, ck, c0, alpha, beta,
+                              gamma, *tile, nullptr, &done, st, add_source, reverse, out_perm);
     if (rc != GSP_OK) return rc;
+    done += front_rows;
     // remainder rows (< rows_per_tile; interior by the fused-form condition)
     return cheby_step<T>(first, done, n, p->indptr, p->indices, static_cast<const T*>(p->data), x_cur,
                          x_old, x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st,
@@ -93,9 +114,21 @@ static int dist_step(const gsp_dist_plan* p, const gsp_tile_plan* tile, bool fus
   }
   int rc = gsp_halo_wait(p->flags, p->neighbor_ids, p->n_neighbors, wait_value, stream);
   if (rc != GSP_OK) return rc;
-  rc = cheby_step<T>(first, 0, n, p->indptr, p->indices, static_cast<const T*>(p->data), x_cur, x_old,
-                     x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st, add_source,
-                     out_perm);
+  int64_t done = 0;
+  if (std::is_same<T, float>::value && tile && tile->rows_per_tile > 0) {
+    // the TMA-tiled kernel without the fused exchange (the halo is complete: the wait kernel
+    // ran), then the row-group kernel on the < rows_per_tile remainder
+    rc = cheby_step_tiled_f32(first, 0, n, p->nnz, p->indptr, p->indices,
+                              reinterpret_cast<const float*>(p->data),
+                              reinterpret_cast<const float*>(x_cur),
+                              reinterpret_cast<const float*>(x_old), reinterpret_cast<float*>(x_new),
+                              reinterpret_cast<float*>(r), r_rows, nsig, nscales, ck, c0, alpha, beta,
+                              gamma, *tile, nullptr, &done, st, add_source, reverse, out_perm);
+    if (rc != GSP_OK) return rc;
+  }
+  rc = cheby_step<T>(first, done, n, p->indptr, p->indices, static_cast<const T*>(p->data), x_cur,
+                     x_old, x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, st,
+                     add_source, out_perm);
   if (rc != GSP_OK) return rc;
   if (publish) return DistTraits<T>::push(p, p->n_send, new_buf, publish_value, nsig, stream);
   return GSP_OK;
@@ -149,7 +182,7 @@ int cheby_op_dist(const gsp_dist_plan* p, const gsp_tile_plan* tile, double lmax
   T* buf[3] = {static_cast<T*>(p->buf[0]), static_cast<T*>(p->buf[1]), static_cast<T*>(p->buf[2])};
   const bool tiled = std::is_same<T, float>::value && tile && tile->rows_per_tile > 0;
   const bool fused =
-      tiled && p->n_neighbors >= 1 && p->n_neighbors <= 32 &&
+      tiled && !p->separate_exchange && p->n_neighbors >= 1 && p->n_neighbors <= 32 &&
       std::max(p->n_push_rows, p->n_boundary_rows) <= (n / tile->rows_per_tile) * tile->rows_per_tile;
   if (clenshaw && (nscales != 1 || K < 2 || !buf[2])) clenshaw = 0;
 

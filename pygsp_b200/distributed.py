@@ -220,6 +220,7 @@ class PartitionedCheby:
         # halo is 3 % faster unsplit).  None = decide per call from the halo size.
         self.overlap = overlap
         self.overlap_min_bytes = 16 << 20
+        self.p2p_max_halo_fraction = 0.25
         t = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(
             np.ascontiguousarray(a))).to(device=self.device, dtype=dt)
         self.indptr = t(plan.indptr, torch.int32)
@@ -265,15 +266,21 @@ class PartitionedCheby:
             mode = self.exchange or "nccl"
         else:
             ok = 1 if self.backend.peers_reachable(self) else 0
-            t = torch.tensor([halo_bytes, -ok], dtype=torch.int64, device=self.device)
+            ratio_ppm = int(1e6 * p.n_halo / max(p.n_local, 1))
+            t = torch.tensor([halo_bytes, -ok, ratio_ppm], dtype=torch.int64, device=self.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            max_halo, all_ok = int(t[0].item()), int(t[1].item()) == -1
+            max_halo, all_ok, max_ratio = int(t[0].item()), int(t[1].item()) == -1, int(t[2].item())
             if self.exchange == "nccl" or not all_ok:
                 mode = "nccl"
             elif self.exchange == "p2p":
                 mode = "p2p"
             else:
-                mode = "p2p" if max_halo < self.overlap_min_bytes else "nccl"
+                # peer stores from the step kernel's epilogue suit a halo that is a thin shell of
+                # the block (k-NN / grid cuts: boundary rows are few and leave first); a halo as
+                # large as the block itself (SBM: every row is a boundary row) moves better as
+                # one packed transfer per peer
+                thin = max_ratio <= int(1e6 * self.p2p_max_halo_fraction)
+                mode = "p2p" if (thin or max_halo < self.overlap_min_bytes) else "nccl"
         self._modes[nsig] = mode
         return mode
 
@@ -461,7 +468,8 @@ class PartitionedCheby:
         xin = x.to(self.dtype).contiguous()
         use_clenshaw = bool(clenshaw) and nscales == 1 and M >= 3
         r = torch.empty((nscales, n, nsig), dtype=self.dtype, device=self.device)
-        plan = self._tile_plan(nsig, nscales) if self.fuse_halo else None
+        plan = self._tile_plan(nsig, nscales)
+        win.dist_plan.separate_exchange = 0 if self.fuse_halo else 1
         seq = ctypes.c_uint64(self._seq)
         # the row permutation (boundary rows first) is applied inside the call: the input is
         # gathered straight into the window, the result is stored to the caller's rows
