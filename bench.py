@@ -676,7 +676,7 @@ def run_ours(args):
         if rank == 0:        # and the engine itself against the float64 oracle on one column
             col = x_full[:, :1].contiguous()
             parity["parity_rel_err_one_column_vs_oracle"] = oracle_parity(G.L, lmax, c, col, single(col))
-    else:
+    elif op is not None:
         # No rank holds the whole graph.  Two size-independent checks on every rank:
         # (1) L 1 = 0, so filtering the constant signal must return p(0) = c_0/2 + sum_k (-1)^k c_k
         #     on every vertex -- a stale or missing halo row breaks it at the boundary rows;

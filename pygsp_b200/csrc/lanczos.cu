@@ -240,6 +240,9 @@ spmv_subwarp_kernel(int64_t n, const int32_t* __restrict__ indptr,
 }
 
 static inline int spmv_lanes_subwarp(int64_t n, int64_t nnz) {
+  const char* e = getenv("GSPB200_SPMV_LPR");
+  if (e && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
+    return atoi(e);
   const double mean = n > 0 ? double(nnz) / double(n) : 1.0;
   int lpr = 2;
   while (lpr < 32 && 2 * lpr <= mean) lpr *= 2;
@@ -273,7 +276,7 @@ static int spmv_launch(int64_t n, int64_t nnz, const int32_t* indptr, const int3
                        const T* vals, const T* x, T* y, const double* norm2_parts, int n_parts,
                        double* beta_out, double* dot_parts, int* blocks_out, cudaStream_t st) {
   const char* form = getenv("GSPB200_SPMV");
-  if (form && strcmp(form, "subwarp") == 0) {
+  if (!(form && strcmp(form, "window") == 0)) {
     const int lpr = spmv_lanes_subwarp(n, nnz);
     const int64_t rpb = (kVecThreads / lpr) * 4;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, rpb),

@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, GPU call 11 (8 GPUs): BASELINE configs[4] (5e7-vertex 3-D k-NN, 128 signals, order 40) and the
+# strong scaling of the 10M-vertex north-star target at 8 GPUs
+N=${1:-8}
+mkdir -p gpurun_out
+run() { # name, env assignments, extra args
+  env $2 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 $3 > gpurun_out/r2_bench_n${N}_$1.json 2> gpurun_out/r2_bench_n${N}_$1.err
+  echo "== $1 rc=$?"; tail -c 300 gpurun_out/r2_bench_n${N}_$1.err | grep -v "^\*\|OMP_NUM" 
+  python - <<PY
+import json
+try:
+    d = json.loads(open('gpurun_out/r2_bench_n${N}_$1.json').read().strip().splitlines()[-1])
+    print('$1', 'ms', round(d['ms_per_step'], 3), 'value', '%.3e' % d['value'], 'frac', round(d['roofline']['frac'], 3), 'e2e', d['e2e'] and round(d['e2e']['ms_per_step'], 2),
+          {k: v for k, v in d.items() if (k.startswith('parity') and k != 'parity_note') or k.startswith('one_gpu') or k.startswith('speedup')}, d['halo'] and (d['halo']['rows_received_per_rank'], d['halo']['exchange'][:5]), d['graph'])
+except Exception as e:
+    print('$1 unparsed', e)
+PY
+}
+run config5 "GSPB200_X=0" "--workload config5"
+run strong "GSPB200_X=0" ""
+[ -n "$WITH_CONFIG4" ] && run config4 "GSPB200_X=0" "--workload config4 --no-e2e"
+exit 0

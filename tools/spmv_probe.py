@@ -29,8 +29,8 @@ def main():
     peak, _ = bench.measured_peak()
     nbytes = 8 * L.nnz + 4 * (G.N + 1) + 8 * G.N
     ref = None
-    for name, env in (("window", {}), ("window_tr512", {"SPMV_TR": "512"}), ("window_tr256", {"SPMV_TR": "256"}),
-                      ("window_tr128", {"SPMV_TR": "128"}), ("subwarp", {"SPMV": "subwarp"})):
+    for name, env in (("subwarp", {}), ("subwarp_lpr16", {"SPMV_LPR": "16"}), ("subwarp_lpr4", {"SPMV_LPR": "4"}),
+                      ("window", {"SPMV": "window"}), ("window_tr128", {"SPMV": "window", "SPMV_TR": "128"})):
         for k, v in env.items():
             os.environ["GSPB200_" + k] = v
         y = L.dot(x)
