@@ -35,6 +35,7 @@
 namespace gsp {
 
 constexpr int kTiledMaxScales = 16;
+constexpr int kTwoPacketDefault = 0;     // see launch_tiled_g (GSPB200_TILE_P2)
 
 struct TileArgs {
   int64_t n_tiles;
@@ -170,44 +171,58 @@ __device__ __forceinline__ float4 gather_f4(const float* __restrict__ xg, int co
   return ldg_f4(p);
 }
 
-// sum_j w_j x_cur[col_j, c0 : c0 + 4] over the stored entries [jb, je) of one row (slab-relative
-// offsets).  The slab offset is a multiple of 4, so groups of four CSR entries are 16-byte
-// aligned in shared memory: one LDS.128 brings four column indices, one four weights.  Slots
-// outside [jb, je) (row head / tail) are predicated off, so the sum runs over the row's entries
-// in stored order.  COH: the row may reference halo columns (boundary tiles of a partitioned
-// step) -- those are read coherently; interior tiles use the plain non-coherent gather only.
-template <int NS, bool COH>
-__device__ __forceinline__ float4 row_gather_sum(const int32_t* __restrict__ sm_col,
-                                                 const float* __restrict__ sm_val, int jb, int je,
-                                                 const float* __restrict__ xg) {
+// sum_j w_j x_cur[col_j, packets of this lane] over the stored entries [jb, je) of one row
+// (slab-relative offsets).  The slab offset is a multiple of 4, so groups of four CSR entries
+// are 16-byte aligned in shared memory: one LDS.128 brings four column indices, one four
+// weights.  Slots outside [jb, je) (row head / tail) are predicated off, so the sum runs over
+// the row's entries in stored order.  A lane owns P float4 packets of the row, 16 G bytes apart
+// (P = 1: G lanes cover the row once; P = 2: G lanes cover it twice, so a row group is a quarter
+// warp for 64 signals and one LDS.128 of CSR entries serves four rows instead of two -- the
+// broadcast read costs one L1 wavefront per quarter warp whatever it delivers).  4 / P entries
+// are in flight per lane at a time (the same 64 bytes either way).
+// COH: the row may reference halo columns (boundary tiles of a partitioned step) -- the tile
+// gathers through L2 then; interior tiles use the plain non-coherent gather only.
+template <int G, int P, bool COH>
+__device__ __forceinline__ void row_gather_sum(const int32_t* __restrict__ sm_col,
+                                               const float* __restrict__ sm_val, int jb, int je,
+                                               const float* __restrict__ xg, float4 (&acc)[P]) {
+  constexpr int NS = 4 * G * P;
+  constexpr int E = 4 / P;                         // entries requested back to back
   const unsigned span = unsigned(je - jb);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int jj = jb & ~3; jj < je; jj += 4) {
     const int4 c4 = *reinterpret_cast<const int4*>(sm_col + jj);
     const float4 w4 = *reinterpret_cast<const float4*>(sm_val + jj);
-    float4 xv[4];
-    bool ok[4];
     const int base = jj - jb;
-    ok[0] = unsigned(base + 0) < span;
-    ok[1] = unsigned(base + 1) < span;
-    ok[2] = unsigned(base + 2) < span;
-    ok[3] = unsigned(base + 3) < span;
     const int cq[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (ok[q]) xv[q] = gather_f4<COH>(xg, cq[q], NS);
     const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (ok[q]) {
-        acc.x = fmaf(wq[q], xv[q].x, acc.x);
-        acc.y = fmaf(wq[q], xv[q].y, acc.y);
-        acc.z = fmaf(wq[q], xv[q].z, acc.z);
-        acc.w = fmaf(wq[q], xv[q].w, acc.w);
+    for (int h = 0; h < P; ++h) {
+      float4 xv[E][P];
+      bool ok[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        ok[e] = unsigned(base + h * E + e) < span;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (ok[e]) xv[e][p] = gather_f4<COH>(xg + p * 4 * G, cq[h * E + e], NS);
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (ok[e]) {
+          const float w = wq[h * E + e];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            acc[p].x = fmaf(w, xv[e][p].x, acc[p].x);
+            acc[p].y = fmaf(w, xv[e][p].y, acc[p].y);
+            acc[p].z = fmaf(w, xv[e][p].z, acc[p].z);
+            acc[p].w = fmaf(w, xv[e][p].w, acc[p].w);
+          }
+        }
       }
     }
   }
-  return acc;
 }
 
 // What a consumer lane needs to process one staged tile.
@@ -222,16 +237,24 @@ struct TileCtx {
   bool vd;                  // direct mode: x_old / r rows come straight from global memory
 };
 
+__device__ __forceinline__ void fma4(float4& d, float w, const float4& v) {
+  d.x = fmaf(w, v.x, d.x);
+  d.y = fmaf(w, v.y, d.y);
+  d.z = fmaf(w, v.z, d.z);
+  d.w = fmaf(w, v.w, d.w);
+}
+
 // The rows of one tile: gather + three-term recurrence + coefficient AXPYs + stores.
 // COH: the tile's rows may reference halo columns (coherent gathers through L2).
-template <int G, bool FIRST, int NSC, bool COH>
+template <int G, bool FIRST, int NSC, bool COH, int P>
 __device__ __forceinline__ void tile_rows(const TileArgs& a, const TileCtx t) {
   constexpr int RP = 32 / G;               // rows in flight per warp
-  constexpr int NS = 4 * G;                // signal columns (compile-time: cheap addressing)
+  constexpr int NS = 4 * G * P;            // signal columns (compile-time: cheap addressing)
+  constexpr int PS = 4 * G;                // column distance between a lane's packets
   const int R = a.rows_per_tile;
   const int NW = a.consumer_warps;
   const int c0 = t.c0;
-  const float* __restrict__ xg = a.x_cur + c0;      // this lane's column packet of x_cur
+  const float* __restrict__ xg = a.x_cur + c0;      // this lane's first column packet of x_cur
   const int nscales = NSC >= 0 ? NSC : a.nscales;
   const float alpha = a.alpha, beta = a.beta, gamma = a.gamma;
   const bool keep_writes = a.keep_writes != 0;
@@ -248,72 +271,85 @@ __device__ __forceinline__ void tile_rows(const TileArgs& a, const TileCtx t) {
     const int off = lr * NS;
     const int jb = t.sm_ptr[lr] - a0;
     const int je = t.sm_ptr[lr + 1] - a0;
-    const float4 xc = ldg_f4(xc_tile + off);
-    // direct mode: this row's x_old and first r / source packet are requested now (streaming
+    float4 xc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) xc[p] = ldg_f4(xc_tile + off + p * PS);
+    // direct mode: this row's x_old and first r / source packets are requested now (streaming
     // loads, no L1 allocation) and consumed after the gather loop, which hides their latency
-    float4 xo_d = make_float4(0.f, 0.f, 0.f, 0.f), r0_d = xo_d;
+    float4 xo_d[P], r0_d[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) xo_d[p] = r0_d[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!FIRST && VD) {
-      xo_d = __ldcs(reinterpret_cast<const float4*>(a.x_old + (r0 + lr) * NS + c0));
-      if (NSC != 0 && nscales > 0)
-        r0_d = __ldcs(reinterpret_cast<const float4*>(a.r + (r0 + lr) * NS + c0));
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        xo_d[p] = __ldcs(reinterpret_cast<const float4*>(a.x_old + (r0 + lr) * NS + c0 + p * PS));
+        if (NSC != 0 && nscales > 0)
+          r0_d[p] = __ldcs(reinterpret_cast<const float4*>(a.r + (r0 + lr) * NS + c0 + p * PS));
+      }
     }
-    const float4 acc = row_gather_sum<NS, COH>(t.sm_col, t.sm_val, jb, je, xg);
-    float4 xn;
-    xn.x = fmaf(alpha, acc.x, beta * xc.x);
-    xn.y = fmaf(alpha, acc.y, beta * xc.y);
-    xn.z = fmaf(alpha, acc.z, beta * xc.z);
-    xn.w = fmaf(alpha, acc.w, beta * xc.w);
-    if (!FIRST) {
-      const float4 xo = VD ? xo_d : *reinterpret_cast<const float4*>(sm_vec + off + c0);
-      xn.x = fmaf(gamma, xo.x, xn.x);
-      xn.y = fmaf(gamma, xo.y, xn.y);
-      xn.z = fmaf(gamma, xo.z, xn.z);
-      xn.w = fmaf(gamma, xo.w, xn.w);
+    float4 acc[P];
+    row_gather_sum<G, P, COH>(t.sm_col, t.sm_val, jb, je, xg, acc);
+    float4 xn[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      xn[p].x = fmaf(alpha, acc[p].x, beta * xc[p].x);
+      xn[p].y = fmaf(alpha, acc[p].y, beta * xc[p].y);
+      xn[p].z = fmaf(alpha, acc[p].z, beta * xc[p].z);
+      xn[p].w = fmaf(alpha, acc[p].w, beta * xc[p].w);
+      if (!FIRST) {
+        const float4 xo =
+            VD ? xo_d[p] : *reinterpret_cast<const float4*>(sm_vec + off + c0 + p * PS);
+        fma4(xn[p], gamma, xo);
+      }
     }
     if (!FIRST && NSC != 0 && a.add_source) {
       // Clenshaw form: the r tiles are read-only source blocks, x_new += sum_i ck_i s_i
 #pragma unroll
       for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
         if (NSC < 0 && i >= nscales) break;
-        const float4 sv =
-            VD ? (i == 0 ? r0_d
-                         : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
-                                                                  (r0 + lr) * NS + c0)))
-               : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
         const float w = a.ck[i];
-        xn.x = fmaf(w, sv.x, xn.x);
-        xn.y = fmaf(w, sv.y, xn.y);
-        xn.z = fmaf(w, sv.z, xn.z);
-        xn.w = fmaf(w, sv.w, xn.w);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const float4 sv =
+              VD ? (i == 0 ? r0_d[p]
+                           : __ldcs(reinterpret_cast<const float4*>(
+                                 a.r + i * r_stride + (r0 + lr) * NS + c0 + p * PS)))
+                 : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0 + p * PS);
+          fma4(xn[p], w, sv);
+        }
       }
     }
-    if (a.out_perm)      // the caller's row order: local row -> original row (uniform branch)
-      store_f4(a.x_new + __ldg(a.out_perm + r0 + lr) * NS + c0, xn, keep_writes);
-    else
-      store_f4(xn_tile + off, xn, keep_writes);
+    if (a.out_perm) {    // the caller's row order: local row -> original row (uniform branch)
+      float* dst = a.x_new + __ldg(a.out_perm + r0 + lr) * NS + c0;
+#pragma unroll
+      for (int p = 0; p < P; ++p) store_f4(dst + p * PS, xn[p], keep_writes);
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) store_f4(xn_tile + off + p * PS, xn[p], keep_writes);
+    }
 #pragma unroll
     for (int i = 0; i < (NSC >= 0 ? NSC : kTiledMaxScales); ++i) {
       if (NSC < 0 && i >= nscales) break;
       if (!FIRST && a.add_source) break;
-      float4 rv;
       const float ck = a.ck[i];
-      if (FIRST) {
-        const float h0 = a.half_c0[i];
-        rv.x = fmaf(ck, xn.x, h0 * xc.x);
-        rv.y = fmaf(ck, xn.y, h0 * xc.y);
-        rv.z = fmaf(ck, xn.z, h0 * xc.z);
-        rv.w = fmaf(ck, xn.w, h0 * xc.w);
-      } else {
-        rv = VD ? (i == 0 ? r0_d
-                          : __ldcs(reinterpret_cast<const float4*>(a.r + i * r_stride +
-                                                                   (r0 + lr) * NS + c0)))
-                : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0);
-        rv.x = fmaf(ck, xn.x, rv.x);
-        rv.y = fmaf(ck, xn.y, rv.y);
-        rv.z = fmaf(ck, xn.z, rv.z);
-        rv.w = fmaf(ck, xn.w, rv.w);
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float4 rv;
+        if (FIRST) {
+          const float h0 = a.half_c0[i];
+          rv.x = fmaf(ck, xn[p].x, h0 * xc[p].x);
+          rv.y = fmaf(ck, xn[p].y, h0 * xc[p].y);
+          rv.z = fmaf(ck, xn[p].z, h0 * xc[p].z);
+          rv.w = fmaf(ck, xn[p].w, h0 * xc[p].w);
+        } else {
+          rv = VD ? (i == 0 ? r0_d[p]
+                            : __ldcs(reinterpret_cast<const float4*>(
+                                  a.r + i * r_stride + (r0 + lr) * NS + c0 + p * PS)))
+                  : *reinterpret_cast<const float4*>(sm_vec + (i + 1) * R * NS + off + c0 + p * PS);
+          fma4(rv, ck, xn[p]);
+        }
+        store_f4(r_tile + i * r_stride + off + p * PS, rv, keep_writes);
       }
-      store_f4(r_tile + i * r_stride + off, rv, keep_writes);
     }
   }
 }
@@ -349,7 +385,7 @@ __device__ __noinline__ void boundary_tile(const TileArgs& a, const TileCtx t, i
     }
     __syncwarp();
   }
-  tile_rows<G, FIRST, NSC, true>(a, t);
+  tile_rows<G, FIRST, NSC, true, 1>(a, t);
   if (t.tile >= a.halo.n_push_tiles) return;
   if (!a.out_perm) {
     const float* xn_tile = a.x_new + t.r0 * NS + t.c0;
@@ -385,8 +421,10 @@ __device__ __noinline__ void boundary_tile(const TileArgs& a, const TileCtx t, i
   }
 }
 
-template <int G, bool FIRST, int NSC, bool HALO>
-__global__ void __launch_bounds__(32 * 17, 2)
+// One packet per lane: 1 + 16 warps per CTA, 2 CTAs per SM (<= 60 registers).  Two packets per
+// lane keep twice the state per lane: 1 + 8 warps, 3 CTAs per SM (<= 75 registers).
+template <int G, bool FIRST, int NSC, bool HALO, int P>
+__global__ void __launch_bounds__(32 * (P == 2 ? 9 : 17), P == 2 ? 3 : 2)
 cheby_step_tiled(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.rows_per_tile;
@@ -511,7 +549,7 @@ cheby_step_tiled(const __grid_constant__ TileArgs a) {
     if (HALO && tile < a.n_front)          // warp-uniform; interior tiles never wait
       boundary_tile<G, FIRST, NSC>(a, t, lane);
     else
-      tile_rows<G, FIRST, NSC, false>(a, t);
+      tile_rows<G, FIRST, NSC, false, P>(a, t);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
   }
@@ -584,13 +622,14 @@ int tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales, gsp_t
   return GSP_OK;
 }
 
-template <int G, int NSC, bool HALO>
+template <int G, int NSC, bool HALO, int P>
 static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cudaStream_t st) {
   const TileLayout lay(a.rows_per_tile, a.slab_cap, a.nsig, a.nscales, first || a.vec_direct,
                        a.stages);
   const int smem = lay.total(a.stages);
   const int threads = 32 * (1 + a.consumer_warps);
-  auto kern = first ? cheby_step_tiled<G, true, NSC, HALO> : cheby_step_tiled<G, false, NSC, HALO>;
+  GSP_REQUIRE(threads <= 32 * (P == 2 ? 9 : 17), "too many consumer warps for this mapping");
+  auto kern = first ? cheby_step_tiled<G, true, NSC, HALO, P> : cheby_step_tiled<G, false, NSC, HALO, P>;
   GSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
   GSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -602,20 +641,24 @@ static int launch_tiled_k(bool first, const TileArgs& a, int blocks_per_sm, cuda
   return GSP_OK;
 }
 
-template <int G, bool HALO>
+template <int G, bool HALO, int P>
 static int launch_tiled_gh(bool first, const TileArgs& a, int bps, cudaStream_t st) {
   switch (a.nscales) {          // common bank widths get the scale loop unrolled
-    case 0: return launch_tiled_k<G, 0, HALO>(first, a, bps, st);
-    case 1: return launch_tiled_k<G, 1, HALO>(first, a, bps, st);
-    case 2: return launch_tiled_k<G, 2, HALO>(first, a, bps, st);
-    default: return launch_tiled_k<G, -1, HALO>(first, a, bps, st);
+    case 0: return launch_tiled_k<G, 0, HALO, P>(first, a, bps, st);
+    case 1: return launch_tiled_k<G, 1, HALO, P>(first, a, bps, st);
+    case 2: return launch_tiled_k<G, 2, HALO, P>(first, a, bps, st);
+    default: return launch_tiled_k<G, -1, HALO, P>(first, a, bps, st);
   }
 }
 
+// G lanes x P packets x 4 columns = nsig.  The boundary tiles of a partitioned step (halo) always
+// take the one-packet mapping; `two` selects the two-packet mapping for the others.
 template <int G>
-static int launch_tiled_g(bool first, const TileArgs& a, bool halo, int bps, cudaStream_t st) {
-  return halo ? launch_tiled_gh<G, true>(first, a, bps, st)
-              : launch_tiled_gh<G, false>(first, a, bps, st);
+static int launch_tiled_g(bool first, const TileArgs& a, bool halo, bool two, int bps,
+                          cudaStream_t st) {
+  if (halo) return launch_tiled_gh<G, true, 1>(first, a, bps, st);
+  if (two && G >= 8) return launch_tiled_gh<(G >= 8 ? G / 2 : G), false, (G >= 8 ? 2 : 1)>(first, a, bps, st);
+  return launch_tiled_gh<G, false, 1>(first, a, bps, st);
 }
 
 // Full tiles of rows [rb, re) of one step (rb % 4 == 0); reports the number of rows done.
@@ -677,12 +720,16 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
     a.half_c0[i] = (first && i < nscales) ? float(0.5 * c0[i]) : 0.f;
   }
   const bool h = halo != nullptr;
+  // two packets per lane (32 / 64 / 128 signals): a CSR read in shared memory serves twice
+  // as many rows; GSPB200_TILE_P2=0 keeps one packet per lane
+  const bool two = !h && nsig >= 32 && env_int("GSPB200_TILE_P2", kTwoPacketDefault) != 0;
+  if (two) a.consumer_warps = std::min(a.consumer_warps, 8);
   switch (nsig) {
-    case 8: return launch_tiled_g<2>(first, a, h, plan.blocks_per_sm, st);
-    case 16: return launch_tiled_g<4>(first, a, h, plan.blocks_per_sm, st);
-    case 32: return launch_tiled_g<8>(first, a, h, plan.blocks_per_sm, st);
-    case 64: return launch_tiled_g<16>(first, a, h, plan.blocks_per_sm, st);
-    case 128: return launch_tiled_g<32>(first, a, h, plan.blocks_per_sm, st);
+    case 8: return launch_tiled_g<2>(first, a, h, false, plan.blocks_per_sm, st);
+    case 16: return launch_tiled_g<4>(first, a, h, false, plan.blocks_per_sm, st);
+    case 32: return launch_tiled_g<8>(first, a, h, two, plan.blocks_per_sm, st);
+    case 64: return launch_tiled_g<16>(first, a, h, two, plan.blocks_per_sm, st);
+    case 128: return launch_tiled_g<32>(first, a, h, two, plan.blocks_per_sm, st);
   }
   return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 8, 16, 32, 64 or 128 (%s)", "nsig");
 }

@@ -693,3 +693,59 @@ def test_clenshaw_is_the_default_for_one_filter(gsp, sensor5k):
     assert relerr_cols(y_ref_order.cpu().numpy(), ref) <= F32_TOL
     got = apx.cheby_op(G, c[0], x.cpu().numpy())                 # free function, NumPy in / out
     assert relerr_cols(got, ref) <= F32_TOL
+
+
+@pytest.mark.parametrize("nsig,nscales", [(64, 1), (32, 1), (128, 1), (64, 3), (32, 6), (16, 1)])
+def test_tiled_lane_mappings_and_staging_modes_give_the_same_bits(gsp, sensor5k, monkeypatch, nsig, nscales):
+    """The tiled step has two lane mappings (one / two float4 packets per lane, GSPB200_TILE_P2)
+    and two ways to bring x_old / r (TMA-staged or direct streaming loads, GSPB200_TILE_VDIR).
+    Per-row sums run in stored CSR order in all of them: forward recurrence and Clenshaw form
+    must agree bit for bit across the four combinations, and with the oracle to 1e-5."""
+    import torch
+    from pygsp_b200.filters import approximations as apx
+    G, L, _ = sensor5k
+    rng = np.random.default_rng(77 + nsig + nscales)
+    x = torch.from_numpy(rng.standard_normal((G.N, nsig)).astype(np.float32)).cuda()
+    c = rng.standard_normal((nscales, 19)) / np.arange(1, 20) ** 2
+    got = {}
+    for p2 in ("0", "1"):
+        for vd in ("0", "1"):
+            monkeypatch.setenv("GSPB200_TILE_P2", p2)
+            monkeypatch.setenv("GSPB200_TILE_VDIR", vd)
+            G.L._plans.clear()
+            fwd = apx.cheby_op_device(G.L, G.lmax, c, x)
+            cl = apx.cheby_clenshaw_device(G.L, G.lmax, c[:1], x)
+            torch.cuda.synchronize()
+            got[(p2, vd)] = (fwd.clone(), cl.clone())
+    base = got[("0", "0")]
+    for key, (fwd, cl) in got.items():
+        assert torch.equal(fwd, base[0]), key
+        assert torch.equal(cl, base[1]), key
+    ref = orc.cheby_op(L, G.lmax, c, x.double().cpu().numpy()).reshape(nscales, G.N, nsig)
+    assert relerr_cols(base[0].cpu().numpy().reshape(-1, nsig), ref.reshape(-1, nsig)) <= F32_TOL
+    assert relerr_cols(base[1].cpu().numpy(), ref[0]) <= 2 * F32_TOL
+
+
+def test_spmv_forms_agree(gsp, monkeypatch):
+    """The SpMV forms (lane groups walking their row, with 8 or 16 lanes per row / the
+    shared-memory x window) against scipy in float64, on a Morton-numbered and on a random graph."""
+    import torch
+    from scipy import sparse
+    rng = np.random.default_rng(9)
+    mats = [gsp.graphs.Sensor(30000, k=10, seed=2, order="morton").L,
+            gsp.graphs.DeviceCSR.from_scipy(sparse.random(5000, 5000, 0.004, random_state=5, format="csr"),
+                                            torch.float32, torch.device("cuda"))]
+    for D in mats:
+        v = torch.from_numpy(rng.standard_normal(D.shape[1]).astype(np.float32)).cuda()
+        out = {}
+        for form, lpr in (("subwarp", None), ("subwarp", "16"), ("window", None)):
+            monkeypatch.setenv("GSPB200_SPMV", form)
+            if lpr:
+                monkeypatch.setenv("GSPB200_SPMV_LPR", lpr)
+            else:
+                monkeypatch.delenv("GSPB200_SPMV_LPR", raising=False)
+            out[(form, lpr)] = D.dot(v).clone()
+        ref = D.to_scipy().astype(np.float64).dot(v.double().cpu().numpy())
+        for key, y in out.items():
+            err = np.abs(y.double().cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-30)
+            assert err <= 2e-6, (key, err)
