@@ -35,7 +35,6 @@
 namespace gsp {
 
 constexpr int kTiledMaxScales = 16;
-constexpr int kTwoPacketDefault = 0;     // see launch_tiled_g (GSPB200_TILE_P2)
 
 struct TileArgs {
   int64_t n_tiles;
@@ -721,8 +720,13 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
   }
   const bool h = halo != nullptr;
   // two packets per lane (32 / 64 / 128 signals): a CSR read in shared memory serves twice
-  // as many rows; GSPB200_TILE_P2=0 keeps one packet per lane
-  const bool two = !h && nsig >= 32 && env_int("GSPB200_TILE_P2", kTwoPacketDefault) != 0;
+  // as many rows; GSPB200_TILE_P2=0 / 1 forces one / two packets per lane.
+  // Measured (profiles/r2_probe_p2_*.jsonl, Clenshaw form with direct vector loads): 64 signals
+  // 8.13 -> 6.97 ms per order-30 call, 128 signals 15.9 -> 12.6 ms, 32 signals 4.80 -> 4.73 ms;
+  // the forward recurrence with TMA-staged vectors is slower with it (8.8 -> 9.3 ms: only two of
+  // the three CTAs fit), so the default follows the form.
+  const bool two = !h && nsig >= 32 &&
+                   env_int("GSPB200_TILE_P2", (a.add_source && a.vec_direct) ? 1 : 0) != 0;
   if (two) a.consumer_warps = std::min(a.consumer_warps, 8);
   switch (nsig) {
     case 8: return launch_tiled_g<2>(first, a, h, false, plan.blocks_per_sm, st);

@@ -243,9 +243,12 @@ static inline int spmv_lanes_subwarp(int64_t n, int64_t nnz) {
   const char* e = getenv("GSPB200_SPMV_LPR");
   if (e && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
     return atoi(e);
+  // about three entries per lane: fewer, longer lane chains and more rows in flight per warp beat
+  // one entry per lane (N = 1e6, 12.4 entries per row, L2-warm: 4 lanes 34 us, 8 lanes 49 us,
+  // 16 lanes 65 us -- profiles/r2_spmv_probe_b.jsonl)
   const double mean = n > 0 ? double(nnz) / double(n) : 1.0;
   int lpr = 2;
-  while (lpr < 32 && 2 * lpr <= mean) lpr *= 2;
+  while (lpr < 32 && 3 * (2 * lpr) <= mean) lpr *= 2;
   return lpr;
 }
 

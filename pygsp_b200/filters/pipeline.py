@@ -38,22 +38,19 @@ def _side_streams(device):
 def chunk_plan(n, nsig, itemsize):
     """Column chunks [(offset, width), ...] for an (n, nsig) block.
 
-    The first upload and the last download cannot overlap any computation, so the first
-    and the last chunk are NARROW (a quarter of the block each) and the middle one wide
-    (half: wide blocks run the recurrence more efficiently): 64 signals -> 16 | 32 | 16.
-    Every width is one the tiled kernel supports; blocks that are small (< 32 MB) or whose
-    width does not split that way are taken whole.  GSPB200_E2E_CHUNK=w forces equal chunks of
-    w signals (0 = no pipelining)."""
+    Two halves: 64 signals -> 32 | 32.  Narrower chunks shorten the first upload and the last
+    download, which overlap nothing, but every chunk re-reads the CSR arrays at every order and
+    narrow blocks run the recurrence less efficiently -- the pipeline is compute-bound, so the
+    halves win (config 2, one box: 16 | 32 | 16 -> 15.8 ms, 32 | 32 -> 14.8 ms, 4 x 16 -> 17.0 ms
+    per call; profiles/r2_e2e_trace.txt has the timelines).  The width must be one the
+    tiled kernel supports; blocks that are small (< 32 MB) or do not split that way are taken
+    whole.  GSPB200_E2E_CHUNK=w forces equal chunks of w signals (0 = no pipelining)."""
     env = os.environ.get("GSPB200_E2E_CHUNK")
     if env is not None:
         w = int(env)
         if w > 0 and nsig % w == 0:
             return [(o, w) for o in range(0, nsig, w)]
         return [(0, nsig)]
-    q = nsig // 4
-    if nsig % 4 == 0 and q in _TILED_WIDTHS and 2 * q in _TILED_WIDTHS \
-            and n * nsig * itemsize >= (32 << 20):
-        return [(0, q), (q, 2 * q), (3 * q, q)]
     h = nsig // 2
     if nsig % 2 == 0 and h in _TILED_WIDTHS and n * nsig * itemsize >= (32 << 20):
         return [(0, h), (h, h)]
