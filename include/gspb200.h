@@ -64,7 +64,8 @@ typedef struct gsp_tile_plan {
   int rows_per_tile;   /* rows of L per shared-memory stage */
   int slab_capacity;   /* CSR entries a stage can hold (>= the matrix's largest tile) */
   int stages;          /* depth of the TMA ring */
-  int consumer_warps;  /* warps that compute (one more warp produces) */
+  int consumer_warps;  /* warps that compute (one more warp produces); the two-packet lane
+                          mapping of the Clenshaw form runs min(consumer_warps, 8) of them */
   int gather_unroll;   /* reserved (always 4: one LDS.128 group of CSR entries) */
   int blocks_per_sm;   /* 0 = as many as fit */
 } gsp_tile_plan;
@@ -75,17 +76,19 @@ int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nsca
 
 /* Halo exchange fused into the tiled float32 step (vertex-partitioned path).  Local rows
  * are ordered boundary-first: rows [0, n_boundary_rows) may reference halo columns
- * (column ids >= n_owned), rows [0, n_push_rows) are needed by some neighbour.  The kernel
- * runs the tiles that hold such rows first.  Only the warps that work on a tile with boundary
- * rows wait until flags[wait_ids[q]] >= wait_value (the neighbours have stored x_cur's halo
- * rows into this GPU; those rows are read through L2, never through the non-coherent
- * path); interior tiles start at once.  Every row < n_push_rows of x_new is stored into
- * peer_base[push_peer[e]][push_row[e], :] for e in [push_ptr[row], push_ptr[row+1]) from
- * the epilogue (peer stores over NVLink).  With publish != 0, publish_value is written to
- * every peer_flags[q] when the last front tile is done -- at that point the pushed rows are
- * visible and nobody on this GPU reads the halo of x_cur any more, so the neighbours may
- * also overwrite it.  All pointers are device pointers; the struct itself is a host
- * struct.  n_push_tiles / n_wait_tiles are filled in by the library. */
+ * (column ids >= n_owned), rows [0, n_push_rows) are needed by some neighbour.  A step is two
+ * launches on the caller's stream.  First the tiles that hold such rows ("front" tiles, a few
+ * dozen): their warps wait until flags[wait_ids[q]] >= wait_value (the neighbours have stored
+ * x_cur's halo rows into this GPU; front tiles gather through L2, never through the
+ * non-coherent path), every row < n_push_rows of x_new is stored into
+ * peer_base[push_peer[e]][push_row[e], :] for e in [push_ptr[row], push_ptr[row+1]) (peer
+ * stores over NVLink) and, with publish != 0, publish_value is written to every
+ * peer_flags[q] when the last front tile is done -- at that point the pushed rows are visible
+ * and nobody on this GPU reads the halo of x_cur any more, so the neighbours may also
+ * overwrite it.  Then all interior tiles, with the plain kernel instantiation (one kernel
+ * for both spilled registers into the interior loop: 1.6 x slower steps).  All pointers are
+ * device pointers; the struct itself is a host struct.  n_push_tiles / n_wait_tiles are
+ * filled in by the library. */
 typedef struct gsp_halo_fusion {
   int64_t n_push_rows;
   int64_t n_push_tiles;

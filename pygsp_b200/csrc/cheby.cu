@@ -33,6 +33,13 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
                          double gamma, const gsp_tile_plan& plan, const gsp_halo_fusion* halo,
                          int64_t* rows_done, cudaStream_t st, bool add_source = false,
                          bool reverse = false, const int64_t* out_perm = nullptr);
+int cheby_step_tiled_halo_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+                              const int32_t* indices, const float* vals, const float* x_cur,
+                              const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
+                              int nscales, const double* ck, const double* c0, double alpha,
+                              double beta, double gamma, const gsp_tile_plan& plan,
+                              const gsp_halo_fusion& halo, int64_t* rows_done, cudaStream_t st,
+                              bool add_source, bool reverse, const int64_t* out_perm);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -506,10 +513,10 @@ int gsp_cheby_step_halo_f32(int first, int64_t n_rows, int64_t nnz, const int32_
     return gsp::fail(GSP_ERR_UNSUPPORTED, "fused halo step needs a tile plan (%s)", "plan");
   GSP_REQUIRE(nscales <= gsp::kMaxScales, "too many filters for the fused step");
   int64_t done = 0;
-  int rc = gsp::cheby_step_tiled_f32(first != 0, 0, n_rows, nnz, indptr, indices, data, x_cur,
-                                     x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
-                                     c0_host, alpha, beta, gamma, *plan_host, halo_host, &done,
-                                     gsp::as_stream(stream), false, reverse != 0);
+  int rc = gsp::cheby_step_tiled_halo_f32(first != 0, n_rows, nnz, indptr, indices, data, x_cur,
+                                          x_old, x_new, r, r_rows, (int)nsig, nscales, ck_host,
+                                          c0_host, alpha, beta, gamma, *plan_host, *halo_host, &done,
+                                          gsp::as_stream(stream), false, reverse != 0, nullptr);
   if (rc != GSP_OK) return rc;
   // remainder rows (< rows_per_tile, interior by construction) with the row-group kernel
   return gsp::cheby_step<float>(first != 0, done, n_rows, indptr, indices, data, x_cur, x_old,

@@ -738,6 +738,41 @@ int cheby_step_tiled_f32(bool first, int64_t rb, int64_t re, int64_t nnz, const 
   return fail(GSP_ERR_UNSUPPORTED, "tiled kernel: nsig must be 8, 16, 32, 64 or 128 (%s)", "nsig");
 }
 
+// One step of the vertex-partitioned path on rows [0, n): two launches on one stream.
+// (1) The boundary ("front") tiles -- those holding rows that read halo columns or that some
+// neighbour needs -- with the halo-capable instantiation: wait for the neighbours' flags, coherent
+// gathers, peer stores of the new boundary rows, publish.  (2) All interior tiles with the plain
+// instantiation.  One kernel for both was 1.6 x slower per step: under the
+// 60-register cap ptxas spilled the boundary code's state inside the interior gather loop.  The
+// front launch is a few dozen tiles (~10 us) and publishes before the interior tiles run, so the
+// neighbours' next front launch finds the flag set.  Reports the rows done (whole tiles).
+int cheby_step_tiled_halo_f32(bool first, int64_t n, int64_t nnz, const int32_t* indptr,
+                              const int32_t* indices, const float* vals, const float* x_cur,
+                              const float* x_old, float* x_new, float* r, int64_t r_rows, int nsig,
+                              int nscales, const double* ck, const double* c0, double alpha,
+                              double beta, double gamma, const gsp_tile_plan& plan,
+                              const gsp_halo_fusion& halo, int64_t* rows_done, cudaStream_t st,
+                              bool add_source, bool reverse, const int64_t* out_perm) {
+  const int64_t R = plan.rows_per_tile;
+  const int64_t front_rows =
+      ceil_div(std::max<int64_t>(halo.publish ? halo.n_push_rows : 0, halo.n_boundary_rows), R) * R;
+  GSP_REQUIRE(front_rows <= (n / R) * R, "boundary rows must lie inside the full tiles");
+  int64_t done_front = 0, done = 0;
+  if (front_rows > 0) {
+    int rc = cheby_step_tiled_f32(first, 0, front_rows, nnz, indptr, indices, vals, x_cur, x_old,
+                                  x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, plan,
+                                  &halo, &done_front, st, add_source, false, out_perm);
+    if (rc != GSP_OK) return rc;
+    GSP_REQUIRE(done_front == front_rows, "front tiles must be whole tiles");
+  }
+  int rc = cheby_step_tiled_f32(first, front_rows, n, nnz, indptr, indices, vals, x_cur, x_old,
+                                x_new, r, r_rows, nsig, nscales, ck, c0, alpha, beta, gamma, plan,
+                                nullptr, &done, st, add_source, reverse, out_perm);
+  if (rc != GSP_OK) return rc;
+  *rows_done = front_rows + done;
+  return GSP_OK;
+}
+
 }  // namespace gsp
 
 extern "C" int gsp_cheby_tile_plan(int64_t n, const int32_t* indptr, int64_t nsig, int nscales,

@@ -388,13 +388,15 @@ class PartitionedCheby:
         self._exchange(buf, 1)
         return self.backend.spmm(self, buf)[:, 0]
 
-    def estimate_lmax(self, method="lanczos", seed=0, tol=5e-3, max_steps=400, polish_steps=60):
+    def estimate_lmax(self, method="lanczos", seed=0, tol=5e-3, max_steps=400, polish_steps=60,
+                      lap_type="combinatorial"):
         """Distributed ``Graph.estimate_lmax`` (graph.py:858-931) for the partitioned L.
 
         'lanczos': the same three-term recurrence and stopping rule as the single-GPU
         engine (``graphs.graph.ritz_check``); the operator is the local SpMM after a halo
         exchange, the two scalars per step are all-reduced.  Returns 1.01 * theta.
-        'bounds': Gershgorin bound 2 max_i L_ii over all ranks (graph.py:943-945).
+        'bounds': the minimum of the reference's four algebraic bounds (graph.py:933-960), the
+        same value ``Graph.estimate_lmax('bounds')`` returns for the assembled graph.
         """
         import torch
         import torch.distributed as dist
@@ -406,17 +408,7 @@ class PartitionedCheby:
                 dist.all_reduce(t, group=self.group)
             return t
         if method == "bounds":
-            rows = torch.arange(p.n_local, device=self.device)
-            diag = torch.zeros(p.n_local, dtype=torch.float64, device=self.device)
-            ptr = self.indptr.long()
-            row_of = torch.repeat_interleave(rows, ptr[1:] - ptr[:-1])
-            on_diag = self.indices.long() == row_of
-            diag.index_add_(0, row_of[on_diag], self.data[on_diag].double())
-            top = 2.0 * diag.max().reshape(1) if p.n_local else torch.zeros(1, dtype=torch.float64,
-                                                                            device=self.device)
-            if p.parts > 1:
-                dist.all_reduce(top, op=dist.ReduceOp.MAX, group=self.group)
-            return float(top.item())
+            return self._upper_bound(lap_type)
         if method != "lanczos":
             raise ValueError("Unknown method {}".format(method))
         gen = torch.Generator(device=self.device).manual_seed(seed * 7919 + p.rank)
@@ -450,6 +442,57 @@ class PartitionedCheby:
         if converged or cap == p.n_global:
             return 1.01 * theta
         raise ValueError("The Lanczos method did not converge. Try to use bounds.")
+
+    def _upper_bound(self, lap_type="combinatorial"):
+        """``Graph._get_upper_bound`` (graph.py:933-960) for the partitioned Laplacian: the minimum
+        of N max W, 2 max dw, max over edges (dw_s + dw_t) and Merris' max(dw + (W dw) / dw) --
+        2 for the normalized Laplacian.  W and dw are read off the rows of L = D - W (graphs
+        without self-loops: L_ii = dw_i, L_ij = -w_ij); the weighted degrees of the halo columns
+        come from one halo exchange, the maxima from all-reduces.  A NaN Merris bound (isolated
+        vertex) is skipped like Python's ``min`` skips a trailing NaN in the reference."""
+        import torch
+        import torch.distributed as dist
+        if lap_type == "normalized":
+            return 2
+        if lap_type != "combinatorial":
+            raise ValueError("Unknown Laplacian type {}".format(lap_type))
+        p = self.plan
+        n = p.n_local
+        dev = self.device
+        ptr = self.indptr.long()
+        row_of = torch.repeat_interleave(torch.arange(n, device=dev), ptr[1:] - ptr[:-1])
+        idx, val = self.indices.long(), self.data.double()
+        on_diag = idx == row_of
+        dw = torch.zeros(n, dtype=torch.float64, device=dev)
+        dw.index_add_(0, row_of[on_diag], val[on_diag])
+        ext = torch.zeros((n + p.n_halo, 1), dtype=self.dtype, device=dev)
+        ext[:n, 0] = dw.to(self.dtype)
+        self._exchange(ext, 1)                           # dw of the halo columns
+        dw_ext = ext[:, 0].double()
+        dw_ext[:n] = dw
+        off = ~on_diag
+        w, r_off, c_off = -val[off], row_of[off], idx[off]
+        neg = torch.full((1,), -float("inf"), dtype=torch.float64, device=dev)
+        has_edges = w.numel() > 0
+        wd = torch.zeros(n, dtype=torch.float64, device=dev)
+        if has_edges:
+            wd.index_add_(0, r_off, w * dw_ext[c_off])
+        isolated = bool((dw == 0).any().item()) if n else False
+        merris = (dw + wd / dw).max().reshape(1) if (n and not isolated) else neg.clone()
+        tops = torch.cat([w.max().reshape(1) if has_edges else neg.clone(),
+                          dw.max().reshape(1) if n else neg.clone(),
+                          (dw[r_off] + dw_ext[c_off]).max().reshape(1) if has_edges else neg.clone(),
+                          merris,
+                          torch.tensor([1.0 if isolated else 0.0], dtype=torch.float64, device=dev)])
+        if p.parts > 1:
+            dist.all_reduce(tops, op=dist.ReduceOp.MAX, group=self.group)
+        w_max, dw_max, edge_max, merris_max, any_isolated = (float(v) for v in tops.tolist())
+        bounds = [p.n_global * w_max if w_max > -float("inf") else 0.0, 2 * dw_max]
+        if edge_max > -float("inf"):
+            bounds.append(edge_max)
+        if not any_isolated:
+            bounds.append(merris_max)
+        return float(min(bounds))
 
     def _cheby_op_p2p(self, lmax, c, x, local_order, clenshaw=False):
         """The whole call is ONE C entry point, ``gsp_cheby_op_dist_*`` (csrc/dist.cu): entry

@@ -111,7 +111,9 @@ def main():
     lam = orc.lambda_max_exact(L)
     est = op.estimate_lmax()
     assert lam * (1 - 2e-4) <= est / 1.01 <= lam * (1 + 1e-5), (est, lam)
-    assert op.estimate_lmax(method="bounds") >= lam
+    bound = op.estimate_lmax(method="bounds")               # the reference's four bounds, distributed
+    assert bound >= lam and abs(bound - orc.upper_bound(W)) <= (1e-5 if backend == "nccl" else 1e-10) * bound
+    assert op.estimate_lmax(method="bounds", lap_type="normalized") == 2
     r = op.cheby_op(lmax, c, xl, clenshaw=False).cpu().numpy().astype(np.float64)
     want = ref[:, lo:hi]
     err = np.abs(r - want).max() / np.abs(ref).max()

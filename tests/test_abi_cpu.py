@@ -115,3 +115,21 @@ def test_ritz_check_on_a_host_lanczos():
     # an exactly invariant start vector: beta_0 = 0 stops at once with the exact eigenvalue
     theta, m, stop, _ = ritz_check(np.array([3.0]), np.array([0.0]), 5e-3, False, False)
     assert stop and m == 1 and theta == 3.0
+
+
+def test_e2e_chunk_plan(monkeypatch):
+    """Column chunks of the pinned-host pipeline (filters/pipeline.py): two halves when the half
+    is a width the tiled kernel takes and the block is worth pipelining, else the whole block;
+    GSPB200_E2E_CHUNK forces equal chunks."""
+    from pygsp_b200.filters import pipeline
+    monkeypatch.delenv("GSPB200_E2E_CHUNK", raising=False)
+    assert pipeline.chunk_plan(1_000_000, 64, 4) == [(0, 32), (32, 32)]
+    assert pipeline.chunk_plan(6_250_000, 128, 4) == [(0, 64), (64, 64)]
+    assert pipeline.chunk_plan(1_000_000, 16, 4) == [(0, 8), (8, 8)]
+    assert pipeline.chunk_plan(1_000_000, 24, 4) == [(0, 24)]          # 12 is not a tiled width
+    assert pipeline.chunk_plan(10_000, 64, 4) == [(0, 64)]             # < 32 MB: not worth it
+    assert pipeline.chunk_plan(1_000_000, 1, 4) == [(0, 1)]
+    monkeypatch.setenv("GSPB200_E2E_CHUNK", "16")
+    assert pipeline.chunk_plan(1_000_000, 64, 4) == [(0, 16), (16, 16), (32, 16), (48, 16)]
+    monkeypatch.setenv("GSPB200_E2E_CHUNK", "0")
+    assert pipeline.chunk_plan(1_000_000, 64, 4) == [(0, 64)]
