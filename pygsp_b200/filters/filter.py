@@ -159,6 +159,14 @@ class Filter:
                              "Nf = {}, got {}.".format(self.Nf, tuple(s.shape)))
         return self.filter(s, method, order)
 
+    def compute_frame(self, **kwargs):
+        r"""Matrix of the analysis operator, (N Nf, N): one delta per vertex through
+        :meth:`filter` (filter.py:540-603; ``method='chebyshev'`` only, like :meth:`filter`)."""
+        if self.G.N > 2000:
+            _logger.warning("Creating a big matrix. You should prefer the filter method.")
+        s = np.identity(self.G.N)
+        return self.filter(s, **kwargs).T.reshape(-1, self.G.N)
+
     def localize(self, i, **kwargs):
         r"""Kernels localised at vertex ``i``: sqrt(N) g(L) delta_i (filter.py:350-391)."""
         delta = np.zeros(self.G.N)

@@ -197,6 +197,8 @@ def test_sensor123_goldens(gsp, golden, dtype):
     assert relerr_cols(F, g["heat89_frame"]) <= tol
     if dtype == np.float64:
         np.testing.assert_allclose(F, g["heat89_frame"], atol=1e-10)
+    F2 = h89.compute_frame(method="chebyshev", order=30)      # filter.py:540-603
+    assert F2.shape == (2 * G.N, G.N) and relerr_cols(F2, g["heat89_frame"]) <= tol
     mh = gsp.filters.MexicanHat(G, Nf=5)
     c = np.array(gsp.filters.compute_cheby_coeff(mh, m=40))
     np.testing.assert_allclose(c, g["mh5_coeff"], rtol=1e-10, atol=1e-13)
