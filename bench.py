@@ -13,7 +13,10 @@ workload, N > 1 : STRONG scaling of the north-star target -- ONE 10M-vertex k-NN
           per recurrence step over NVLink peer memory; every line carries `parity_rel_err`
           (partitioned result vs the single-GPU engine on the whole graph, every rank) and the
           one-GPU time of the same graph measured in the same run.  --scaling weak = 1e6
-          vertices per GPU (strips of one k-NN graph).
+          vertices per GPU (strips of one k-NN graph); --workload config5 = BASELINE configs[4]
+          (5e7-vertex 3-D k-NN, 128 signals, order 40; every rank generates its slab on its
+          GPU), --workload config4 = configs[3] (SBM); their lines carry the constant-signal
+          property and a cross-check of the two exchange transports instead.
 A "step" is one complete cheby_op call (order fused recurrence kernels).
 
 value   : CUDA-event time of K calls with graph + signals resident in HBM.
@@ -21,9 +24,10 @@ e2e     : the same metric through Filter.filter() with HOST (pinned) signals --
           H2D and D2H copies inside the timed region.
 roofline: algorithmic bytes of the recurrence / measured kernel time vs the
           measured HBM copy bandwidth (MEASURED_PEAKS.json).
-cpu_baseline: the oracle port of the reference's scipy path on a bounded sample.
---impl reference: the reference's CPU path (oracle port; the reference itself is
-          Python and cannot travel to the GPU box) on all host cores.
+cpu_baseline: the unmodified reference (baseline/_ref; the oracle port if absent) on one core,
+          a bounded sample of the same workload.
+--impl reference: the unmodified reference's CPU path on up to 64 host processes
+          (one signal column each; the reference is single-threaded by construction).
 """
 import argparse
 import json
