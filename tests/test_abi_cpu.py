@@ -1,7 +1,11 @@
 """CPU-side checks: the C-ABI library builds, loads and exports every symbol the
 header declares; host-side logic that needs no GPU."""
+import os
+
 import numpy as np
 import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def test_library_exports_every_declared_symbol():
@@ -133,3 +137,31 @@ def test_e2e_chunk_plan(monkeypatch):
     assert pipeline.chunk_plan(1_000_000, 64, 4) == [(0, 16), (16, 16), (32, 16), (48, 16)]
     monkeypatch.setenv("GSPB200_E2E_CHUNK", "0")
     assert pipeline.chunk_plan(1_000_000, 64, 4) == [(0, 64)]
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/gspb200.h is a C header (extern "C" boundary: plain pointers and sizes, no C++ or
+    torch types), and examples/c_host.c -- a host written in C -- compiles and links against the
+    built library.  (It needs a GPU to run; here it must fail cleanly at its first cudaMalloc.)"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(HERE)
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(root, "include", "gspb200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    from pygsp_b200 import build
+    lib = build.build()
+    cuda_lib = "/usr/local/cuda/lib64"
+    if not os.path.exists(os.path.join(cuda_lib, "libcudart.so")):
+        pytest.skip("no libcudart to link the example against")
+    exe = str(tmp_path / "c_host")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_host.c"), "-o", exe,
+                    "-L" + os.path.dirname(lib), "-lgspb200", "-L" + cuda_lib, "-lcudart", "-lm",
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 1 and "cudaMalloc failed" in out.stderr
