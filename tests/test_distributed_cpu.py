@@ -128,18 +128,20 @@ def test_knn_slabs_reject_thin_slabs():
         KnnSlabs(0, 8, 50, dim=3, k=16, seed=0, backend="host")
 
 
-def test_halo_plan_from_tensors_equals_host_plan():
-    """HaloPlan.from_device (torch ops, here on CPU tensors) builds the plan of HaloPlan()."""
+@pytest.mark.parametrize("parts,density", [(3, 0.02), (1, 0.02), (4, 0.3), (2, 0.0)])
+def test_halo_plan_from_tensors_equals_host_plan(parts, density):
+    """HaloPlan.from_device (torch ops, here on CPU tensors) builds the plan of HaloPlan():
+    thin halos, a single part (no halo), a dense block (every row a boundary row), no edges."""
     import torch
     from scipy import sparse
     from pygsp_b200 import distributed as gd
     n = 400
-    A = sparse.random(n, n, 0.02, random_state=1, format="csr")
+    A = sparse.random(n, n, density, random_state=1, format="csr")
     A = (A + A.T).tocsr()
     A.sort_indices()
-    bounds = gd.even_bounds(n, 3)
+    bounds = gd.even_bounds(n, parts)
     fake = lambda h, rc, rank, P, g: (np.zeros(0, dtype=np.int64), np.zeros(P, dtype=np.int64))
-    for r in range(3):
+    for r in range(parts):
         rows = A[bounds[r]:bounds[r + 1]]
         p1 = gd.HaloPlan(rows, bounds, r, exchange_ids=fake)
         p2 = gd.HaloPlan.from_device(torch.from_numpy(rows.indptr), torch.from_numpy(rows.indices),
